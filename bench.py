@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""
+bench.py - backbones/sec of the reverse-diffusion sampler (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus 1 ...             # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N > 1
+
+One "step" = one pass of the hot path over one batch: the full T-step p_sample loop (T = 1000,
+cosine schedule) on 512 chains of lengths 50..127 (BASELINE config 2, "foldingdiff_cath BERT,
+batch=512, len 50-128, T=1000") with synthetic weights of the production architecture (the real
+checkpoint is not available offline) and synthetic wrapped-Gaussian noise.
+
+  value  whole-job backbones/s with the initial noise already resident in HBM
+  e2e    the same through the public API with HOST buffers: sampling.p_sample_loop(host noise) ->
+         host tensor; H2D of the noise and D2H of the result inside the timed region
+  roofline / kernels  per-kernel device times measured live with CUDA events (fd_profile_*)
+  cpu_baseline  the oracle port (torch CPU fp32 restatement + the reference's loop arithmetic)
+         timed on this box's host cores on a bounded sample, extrapolated to T steps
+Multi-GPU: chains are independent -> each rank runs 512 chains (weak scaling), no collective inside
+the loop, one NCCL all-gather of the final angles per pass (inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from foldingdiff_b200 import beta_schedules, datasets, synthetic  # noqa: E402
+
+SEED = 7344
+PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
+FALLBACK_PEAK_TFLOPS = 1590.0  # /opt/skills/guides/B200_PROFILING.md fallback (burst)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--workload", choices=["config2", "config3", "config5"], default="config2")
+    p.add_argument("--timesteps", type=int, default=1000)
+    p.add_argument("--batch", type=int, default=None, help="chains per GPU (default: the workload's)")
+    p.add_argument("--gemm", choices=["tc3x", "fp32", "tc1x"], default=os.environ.get("FOLDINGDIFF_B200_GEMM", "tc3x"))
+    p.add_argument("--e2e-history", choices=["full", "final"], default="full")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-chains", type=int, default=64)
+    p.add_argument("--cpu-steps", type=int, default=3)
+    p.add_argument("--profile-steps", type=int, default=20, help="reverse steps of the CUDA-event kernel profile")
+    return p.parse_args()
+
+
+def workload(args):
+    """-> (lengths per GPU, n_pad, start_t, wrap_all, name)"""
+    T = args.timesteps
+    if args.workload == "config2":
+        B = args.batch or 512
+        lengths = synthetic.sweep_lengths(B)
+        return lengths, max(lengths), T, False, f"foldingdiff_cath BERT (synthetic weights), batch={B}/GPU, len 50-127, T={T}"
+    if args.workload == "config3":
+        B = args.batch or 4096
+        return [128] * B, 128, T, False, f"foldingdiff_cath (synthetic weights), batch={B}/GPU, len=128, T={T}"
+    B = args.batch or 512
+    return [128] * B, 128, min(250, T), True, f"partial_noise_reconstruct (synthetic weights/inputs), batch={B}/GPU, len=128, from t={min(250, T)}"
+
+
+def initial_noise(B, n_pad, T):
+    d = datasets.NoisedAnglesDataset(datasets.AnglesEmptyDataset("canonical-full-angles", pad=128),
+                                     timesteps=T, beta_schedule="cosine")
+    torch.manual_seed(SEED)
+    return d, d.sample_noise(torch.zeros(B, 128, 6))[:, :n_pad].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
+    """backbones/s of the reference's CPU path, from a bounded sample extrapolated to T steps."""
+    from oracle import forward as ofwd  # the one place bench.py may execute oracle/
+    from oracle import loop as oloop
+    from oracle import schedules as osched
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic.synthetic_state_dict(synthetic.PRODUCTION, seed=0)
+    model = ofwd.OracleModel(sd, ofwd.OracleConfig(**synthetic.PRODUCTION), [True] * 6).eval()
+    stride = max(1, len(lengths) // chains)
+    sub = [lengths[i] for i in range(0, len(lengths), stride)][:chains]
+    betas = osched.betas_for("cosine", T)
+    g = torch.Generator().manual_seed(SEED)
+    x = oloop.wrap(torch.randn(len(sub), n_pad, 6, generator=g))
+    t_hi = start_t
+    oloop.p_sample_loop(model, sub, x, T, betas, [True] * 6, start_t=1, wrap_all=wrap_all)  # warm-up step
+    t0 = time.perf_counter()
+    # per-step cost does not depend on t: time `steps` reverse steps, extrapolate to the full loop
+    x1 = x
+    for k in range(steps):
+        x1 = oloop.p_sample(model, x1, torch.full((len(sub),), t_hi - 1 - k, dtype=torch.long), sub, betas)
+        x1 = oloop.wrap(x1)
+    dt = (time.perf_counter() - t0) / steps
+    rate = len(sub) / (dt * start_t)
+    sample = (f"{len(sub)} chains (every {stride}-th of the workload's lengths, sum len {sum(sub)}), {steps} reverse steps "
+              f"timed after 1 warm-up at {dt:.3f} s/step, extrapolated x{start_t} steps")
+    return rate, cores, sample, dt
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    lengths, n_pad, start_t, wrap_all, wl_name = workload(args)
+    T = args.timesteps
+    B = len(lengths)
+    flops_step = synthetic.algorithmic_flops(synthetic.PRODUCTION, lengths)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rate, cores, sample, dt = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, max(1, args.cpu_steps), start_t, wrap_all)
+        # each bench "step" of this arm is the bounded sample; W warm-ups + K timed repeats of it
+        reps = []
+        for i in range(args.warmup + args.steps):
+            r, _, _, d = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, 1, start_t, wrap_all)
+            if i >= args.warmup:
+                reps.append(r)
+        value = float(np.mean(reps)) if reps else rate
+        line = {
+            "impl": "reference", "metric": "backbones/sec", "value": value, "unit": "backbones/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * args.cpu_chains / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "timesteps": T, "note": "CPU path: fp32 torch restatement of the reference forward "
+                       "(HF 4.11.3 encoder not installable) + the reference's loop arithmetic"},
+            "cpu_baseline": {"value": value, "unit": "backbones/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "backbones/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------------------------------------
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
+    from foldingdiff_b200 import distributed as fdist
+    from foldingdiff_b200 import modelling, sampling
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = modelling.BertConfig(**synthetic.PRODUCTION)
+    model = modelling.BertForDiffusionBase(cfg, ft_is_angular=[True] * 6, gemm=args.gemm)
+    model.load_state_dict(synthetic.synthetic_state_dict(synthetic.PRODUCTION, seed=0))
+    model = model.to(dev)
+    eng = model.native_engine()
+    dset, noise_host = initial_noise(B, n_pad, T)
+    noise_host = noise_host.pin_memory()
+    betas = dset.alpha_beta_terms["betas"]
+    wrap = [True] * 6
+    eng.set_schedule(betas, T)
+    eng.set_batch(lengths, n_pad)
+    noise_dev = noise_host.to(dev)
+    gather = [torch.empty((B, n_pad, 6), device=dev) for _ in range(world)] if world > 1 else None
+
+    def one_pass_device():
+        x = noise_dev.clone()
+        sampling._run_steps(eng, x, start_t, wrap, None)
+        if world > 1:
+            dist.all_gather(gather, x)  # the job's only collective: finished angles
+        return x
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        one_pass_device()
+    launches0 = eng.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(one_pass_device, args.steps)
+    launches = eng.launch_count() - launches0
+    clocks = clk.summary()
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step / 1000.0)
+
+    # ---- e2e: host noise in, host result out, through the public API ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hist_mode = args.e2e_history
+
+        def one_pass_e2e():
+            if wrap_all:
+                out = sampling.denoise_from(model, noise_host, lengths, start_t, betas).cpu()
+            else:
+                out = sampling.p_sample_loop(model, lengths, noise_host, T, betas, is_angle=wrap, history=hist_mode)
+            return out
+
+        one_pass_e2e()  # allocator warm-up for the history buffers
+        ms_e = timed(one_pass_e2e, args.steps) / args.steps
+        steps_out = start_t if (hist_mode == "full" and not wrap_all) else 1
+        e2e = {"value": world * B / (ms_e / 1000.0), "unit": "backbones/s",
+               "h2d_bytes_per_step": int(noise_host.numel() * 4),
+               "d2h_bytes_per_step": int(steps_out * B * n_pad * 6 * 4),
+               "ms_per_step": ms_e, "api": "sampling.p_sample_loop(host noise) -> host tensor, history=" + hist_mode}
+
+    # ---- per-kernel device times (CUDA events on the launch stream), rank 0 only -------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        nprof = min(args.profile_steps, start_t)
+        x = noise_dev.clone()
+        z = torch.randn((nprof, B, n_pad, 6), device=dev)
+        torch.cuda.synchronize()
+        eng.profile_begin()
+        eng.p_sample_steps(x, start_t, start_t - nprof, z, None, wrap)
+        prof = eng.profile_end()
+        total = sum(v[0] for v in prof.values()) or 1.0
+        kernels = {k: {"ms_per_reverse_step": v[0] / nprof, "launches_per_reverse_step": v[1] / nprof,
+                       "share": v[0] / total} for k, v in prof.items() if v[1]}
+        n = np.asarray(lengths, dtype=np.float64)
+        H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        gemm_flops = {"gemm_qkv": L * 6 * H * H * n.sum(), "gemm_attn_out": L * 2 * H * H * n.sum(),
+                      "gemm_ffn1": L * 2 * H * I * n.sum(), "gemm_ffn2": L * 2 * H * I * n.sum(),
+                      "gemm_head": 2 * H * H * n.sum()}
+        att_flops = L * 6 * H * (n * n).sum()
+        peak_tf, peak_src = FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md)"
+        if os.path.isfile(PEAKS_FILE):
+            with open(PEAKS_FILE) as f:
+                pk = json.load(f)
+            peak_tf, peak_src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+        gemm_ms = sum(prof[k][0] for k in gemm_flops) / nprof
+        gemm_tf = sum(gemm_flops.values()) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        att_ms = prof["attention"][0] / nprof
+        att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+        dominant = "projection GEMMs (tc_gemm_kernel / sgemm_tn_kernel)" if gemm_ms >= att_ms else "attention_simt_kernel"
+        dom_tf = gemm_tf if gemm_ms >= att_ms else att_tf
+        roofline = {"bound": "tensor", "kernel": dominant, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": dom_tf / peak_tf, "peak_source": peak_src, "traffic": None,
+                    "gemm_tflops_algorithmic": gemm_tf, "attention_tflops_algorithmic": att_tf,
+                    "whole_step_tflops_algorithmic": flops_step * start_t / (ms_per_step * 1e-3) / 1e12,
+                    "note": "algorithmic FLOPs (valid tokens, 2 flop/MAC, SURVEY 8d) / CUDA-event kernel time; "
+                            "the 3-pass split issues 3x these MMAs"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample, _ = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, args.cpu_steps, start_t, wrap_all)
+        cpu_baseline = {"value": rate, "unit": "backbones/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "backbones/sec", "value": value, "unit": "backbones/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": {"tc3x": "f32 (fp16 hi/lo 3-pass tensor-core GEMMs, fp32 accumulate)",
+                                                              "fp32": "f32", "tc1x": "f16 (single-pass, NOT parity mode)"}[args.gemm],
+            "data": "synthetic",
+            "config": {"workload": wl_name, "timesteps": T, "reverse_steps_per_pass": start_t, "chains_per_gpu": B,
+                       "gemm": args.gemm, "parallelism": f"dp{world} (independent chains, one all-gather of final angles)",
+                       "l2": "inputs larger than L2: ~1 GB of activations per reverse step, 1000 steps per pass",
+                       "algorithmic_tflop_per_pass": flops_step * start_t / 1e12},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

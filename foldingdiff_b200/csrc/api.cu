@@ -1,0 +1,613 @@
+// C ABI of foldingdiff_b200 (see include/foldingdiff_b200.h): handle, weight packing, per-batch
+// packed-row bookkeeping, workspace, and the launch sequence of one reverse-diffusion step.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/foldingdiff_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_simt.cuh"
+#include "philox.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define FD_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(FD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),     \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+struct LayerW {
+  float *w_qkv, *b_qkv, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
+  fd::TcWeight tq, to, ti, to2;  // tensor-core operand planes (hi / lo) of the four projections
+};
+
+}  // namespace
+
+struct fd_handle {
+  fd_dims d;
+  int device = 0;
+  int gemm_mode = FD_GEMM_FP32_SIMT;
+  int sm_count = 148;
+  std::vector<void*> allocs;  // everything cudaMalloc'ed for weights / tables
+  float *w_in = nullptr, *b_in = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<LayerW> layers;
+  float *w_d1 = nullptr, *b_d1 = nullptr, *hln_g = nullptr, *hln_b = nullptr, *w_d2 = nullptr,
+        *b_d2 = nullptr;
+  fd::TcWeight td1;
+  float* time_table = nullptr;  // (T, H) device
+  std::vector<float> coef;      // (T, 4) host
+
+  // batch state
+  int batch = 0, n_pad = 0, rows = 0, rows_pad = 0, all_rows = 0;
+  bool has_key_bias = false;
+  int cap_batch = 0, cap_rows = 0, cap_bn = 0;
+  int *row_src = nullptr, *row_start = nullptr, *n_rows = nullptr, *n_keys = nullptr;
+  float* key_bias = nullptr;
+  // workspace (rows_pad x width), fp32
+  float *h = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *a = nullptr, *inter = nullptr;
+  fd::TcActs tc;  // hi / lo operand planes of the activations (tensor-core modes)
+  long long launches = 0;
+  // optional CUDA-event profiler (fd_profile_begin / fd_profile_end)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs: start, stop
+  std::vector<int> prof_cat;         // category of each pair
+  size_t prof_used = 0;
+};
+
+namespace {
+
+enum { CAT_EMBED = 0, CAT_GEMM_QKV, CAT_ATTN, CAT_GEMM_OUT, CAT_LN, CAT_GEMM_FFN1, CAT_GEMM_FFN2,
+       CAT_GEMM_HEAD, CAT_TAIL, CAT_SPLIT, CAT_COUNT };
+const char* const kCatNames[CAT_COUNT] = {"embed", "gemm_qkv", "attention", "gemm_attn_out", "layernorm",
+                                          "gemm_ffn1", "gemm_ffn2", "gemm_head", "tail_posterior", "split"};
+
+// Records a CUDA-event pair around one kernel launch when profiling is on (events on the launch stream).
+struct ProfScope {
+  fd_handle* h; cudaStream_t st; cudaEvent_t stop = nullptr;
+  ProfScope(fd_handle* H, int cat, cudaStream_t s) : h(H), st(s) {
+    if (!h || !h->prof_on) return;
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+    }
+    cudaEvent_t start = h->prof_ev[h->prof_used];
+    stop = h->prof_ev[h->prof_used + 1];
+    h->prof_used += 2;
+    h->prof_cat.push_back(cat);
+    cudaEventRecord(start, st);
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+
+int dev_alloc(fd_handle* h, void** p, size_t bytes) {
+  FD_CUDA(cudaMalloc(p, bytes));
+  h->allocs.push_back(*p);
+  return FD_OK;
+}
+
+int upload(fd_handle* h, float** dst, const float* src, size_t n) {
+  int rc = dev_alloc(h, (void**)dst, n * sizeof(float));
+  if (rc) return rc;
+  FD_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return FD_OK;
+}
+
+void free_batch(fd_handle* h) {
+  cudaFree(h->row_src); cudaFree(h->row_start); cudaFree(h->n_rows); cudaFree(h->n_keys);
+  cudaFree(h->key_bias);
+  cudaFree(h->h); cudaFree(h->qkv); cudaFree(h->ctx); cudaFree(h->tmp); cudaFree(h->a);
+  cudaFree(h->inter);
+  fd::tc_free_acts(&h->tc);
+  h->row_src = h->row_start = h->n_rows = h->n_keys = nullptr;
+  h->key_bias = nullptr;
+  h->h = h->qkv = h->ctx = h->tmp = h->a = h->inter = nullptr;
+  h->cap_batch = h->cap_rows = h->cap_bn = 0;
+}
+
+template <int VPL>
+void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
+  const int blocks = (H->rows * 32 + 255) / 256;
+  ProfScope ps(H, CAT_EMBED, st);
+  fd::embed_kernel<VPL><<<blocks, 256, 0, st>>>(x, H->row_src, H->rows, H->n_pad, H->d.n_features,
+                                                H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps,
+                                                temb, temb_stride, H->h);
+  H->launches++;
+}
+
+template <int VPL>
+void launch_ln(fd_handle* H, const float* in, const float* g, const float* b, float* out,
+               cudaStream_t st) {
+  const int blocks = (H->rows * 32 + 255) / 256;
+  ProfScope ps(H, CAT_LN, st);
+  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, H->rows, g, b, H->d.ln_eps, out);
+  H->launches++;
+}
+
+void launch_sgemm(fd_handle* H, int epi, const float* A, const float* W, const float* bias,
+                  const float* resid, float* C, int M, int N, int K, cudaStream_t st) {
+  dim3 grid(N / 64, M / 128);
+  switch (epi) {
+    case fd::EPI_BIAS:
+      fd::sgemm_tn_kernel<fd::EPI_BIAS><<<grid, 256, 0, st>>>(A, W, bias, resid, C, M, N, K);
+      break;
+    case fd::EPI_BIAS_GELU:
+      fd::sgemm_tn_kernel<fd::EPI_BIAS_GELU><<<grid, 256, 0, st>>>(A, W, bias, resid, C, M, N, K);
+      break;
+    default:
+      fd::sgemm_tn_kernel<fd::EPI_BIAS_RESID><<<grid, 256, 0, st>>>(A, W, bias, resid, C, M, N, K);
+  }
+  if (H) H->launches++;
+}
+
+size_t attn_smem_bytes(int n_rows, int n_keys) {
+  return sizeof(float) * ((size_t)2 * n_keys * FD_HEAD_DIM + (size_t)(n_rows + n_keys - 1) * (FD_HEAD_DIM + 1) + n_keys);
+}
+
+void launch_attention(fd_handle* H, const float* dist, cudaStream_t st) {
+  dim3 grid(H->d.heads, H->batch);
+  const size_t smem = attn_smem_bytes(H->n_pad, H->n_pad);
+  ProfScope ps(H, CAT_ATTN, st);
+  fd::attention_simt_kernel<<<grid, 128, smem, st>>>(H->qkv, H->row_start, H->n_rows, H->n_keys,
+                                                     H->has_key_bias ? H->key_bias : nullptr,
+                                                     H->n_pad, dist, H->d.max_pos, H->d.hidden, H->ctx);
+  H->launches++;
+}
+
+template <int VPL, bool SAMPLE>
+void launch_tail(fd_handle* H, float* eps_out, float* x, const float* z, float* hist,
+                 fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st) {
+  const int blocks = (H->rows * 32 + 255) / 256;
+  const size_t smem = sizeof(float) * H->d.n_features * H->d.hidden;
+  ProfScope ps(H, CAT_TAIL, st);
+  fd::tail_kernel<VPL, SAMPLE><<<blocks, 256, smem, st>>>(
+      H->tmp, H->row_src, H->rows, H->d.n_features, H->hln_g, H->hln_b, H->d.head_ln_eps, H->w_d2,
+      H->b_d2, eps_out, x, z, hist, coef, wrap_bits);
+  H->launches++;
+}
+
+// One projection  C = A W^T + bias (+resid)(+gelu)  in the handle's arithmetic.
+// `a_tc` / `c_tc` are the tensor-core operand planes that shadow A / C (nullptr where unused).
+int project(fd_handle* H, int cat, int epi, const float* A, const float* W, const fd::TcWeight* tw,
+            const float* bias, const float* resid, float* C, int N, int K, const fd::TcPlane* a_tc,
+            fd::TcPlane* c_tc, cudaStream_t st) {
+  ProfScope ps(H, cat, st);
+  if (H->gemm_mode == FD_GEMM_FP32_SIMT) {
+    launch_sgemm(H, epi, A, W, bias, resid, C, H->rows_pad, N, K, st);
+    return FD_OK;
+  }
+  int rc = fd::tc_gemm(H->gemm_mode, epi, a_tc, tw, bias, resid, C, c_tc, H->rows_pad, N, K,
+                       H->sm_count, st);
+  if (rc != 0) return fail(FD_ERR_CUDA, "tensor-core GEMM launch failed (%d)", rc);
+  H->launches++;
+  return FD_OK;
+}
+
+// The noise-predictor forward on the current batch: leaves gelu(dense1(h_L)) in H->tmp.
+template <int VPL>
+int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
+  const int Hd = H->d.hidden, I = H->d.intermediate;
+  const bool tcm = H->gemm_mode != FD_GEMM_FP32_SIMT;
+  launch_embed<VPL>(H, x, temb, temb_stride, st);
+  if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->h, &H->tc.h, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+  for (int l = 0; l < H->d.layers; ++l) {
+    LayerW& w = H->layers[l];
+    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, w.b_qkv, nullptr, H->qkv, 3 * Hd, Hd,
+                     &H->tc.h, nullptr, st);
+    if (rc) return rc;
+    launch_attention(H, w.dist, st);
+    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->ctx, &H->tc.ctx, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+    rc = project(H, CAT_GEMM_OUT, fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp, Hd, Hd,
+                 &H->tc.ctx, nullptr, st);
+    if (rc) return rc;
+    launch_ln<VPL>(H, H->tmp, w.ln1_g, w.ln1_b, H->a, st);
+    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->a, &H->tc.a, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+    rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, H->inter, I, Hd,
+                 &H->tc.a, &H->tc.inter, st);
+    if (rc) return rc;
+    rc = project(H, CAT_GEMM_FFN2, fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a, H->tmp, Hd, I,
+                 &H->tc.inter, nullptr, st);
+    if (rc) return rc;
+    launch_ln<VPL>(H, H->tmp, w.ln2_g, w.ln2_b, H->h, st);
+    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->h, &H->tc.h, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+  }
+  return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, &H->td1, H->b_d1, nullptr, H->tmp, Hd, Hd,
+                 &H->tc.h, nullptr, st);
+}
+
+int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FD_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fd_num_weights(int32_t layers) { return FD_W_HEAD + FD_W_PER_LAYER * layers + FD_W_TAIL; }
+
+int32_t fd_abi_version(void) { return FD_ABI_VERSION; }
+
+const char* fd_build_info(void) {
+  return "foldingdiff_b200 sm_100a; gemm: fp32-simt, tcgen05-3x, tcgen05-1x; attention: fp32-simt";
+}
+
+const char* fd_last_error(void) { return g_err.c_str(); }
+
+int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_weights,
+                  const float* time_table, const float* coef, int32_t device, int32_t gemm_mode,
+                  fd_handle** out) {
+  if (!dims || !weights || !time_table || !coef || !out) return fail(FD_ERR_INVALID, "null argument");
+  const fd_dims& d = *dims;
+  if (d.hidden % 64 || d.hidden > 512 || d.hidden < 64)
+    return fail(FD_ERR_UNSUPPORTED, "hidden=%d must be a multiple of 64 in [64, 512]", d.hidden);
+  if (d.heads <= 0 || d.hidden != d.heads * FD_HEAD_DIM)
+    return fail(FD_ERR_UNSUPPORTED, "head_dim must be %d (hidden=%d heads=%d)", FD_HEAD_DIM, d.hidden, d.heads);
+  if (d.intermediate % 64) return fail(FD_ERR_UNSUPPORTED, "intermediate=%d must be a multiple of 64", d.intermediate);
+  if (d.max_pos < 1 || d.max_pos > 128) return fail(FD_ERR_UNSUPPORTED, "max_pos=%d must be in [1, 128]", d.max_pos);
+  if (d.n_features < 1 || d.n_features > FD_MAX_FEATURES) return fail(FD_ERR_UNSUPPORTED, "n_features=%d", d.n_features);
+  if (d.layers < 1 || d.timesteps < 1) return fail(FD_ERR_INVALID, "layers/timesteps must be positive");
+  if (n_weights != fd_num_weights(d.layers))
+    return fail(FD_ERR_INVALID, "expected %d weight tensors, got %d", fd_num_weights(d.layers), n_weights);
+  if (gemm_mode < FD_GEMM_FP32_SIMT || gemm_mode > FD_GEMM_TC_1X) return fail(FD_ERR_INVALID, "bad gemm_mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(FD_ERR_CUDA, "no CUDA device visible: foldingdiff_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(FD_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  FD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(FD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  FD_CUDA(cudaSetDevice(device));
+
+  fd_handle* h = new fd_handle();
+  h->d = d;
+  h->device = device;
+  h->gemm_mode = gemm_mode;
+  h->sm_count = prop.multiProcessorCount;
+  const int H = d.hidden, I = d.intermediate, F = d.n_features;
+  int rc = FD_OK;
+#define UP(dst, idx, n) if (!rc) rc = upload(h, &(dst), weights[idx], (size_t)(n))
+  UP(h->w_in, 0, H * F); UP(h->b_in, 1, H); UP(h->emb_g, 2, H); UP(h->emb_b, 3, H);
+  h->layers.resize(d.layers);
+  for (int l = 0; l < d.layers && !rc; ++l) {
+    const int b = FD_W_HEAD + l * FD_W_PER_LAYER;
+    LayerW& w = h->layers[l];
+    // fused QKV: rows [0,H) = query, [H,2H) = key, [2H,3H) = value
+    rc = dev_alloc(h, (void**)&w.w_qkv, sizeof(float) * 3 * H * H);
+    if (!rc) rc = dev_alloc(h, (void**)&w.b_qkv, sizeof(float) * 3 * H);
+    for (int j = 0; j < 3 && !rc; ++j) {
+      if (cudaMemcpy(w.w_qkv + (size_t)j * H * H, weights[b + 2 * j], sizeof(float) * H * H, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(w.b_qkv + (size_t)j * H, weights[b + 2 * j + 1], sizeof(float) * H, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(FD_ERR_CUDA, "weight upload failed");
+    }
+    UP(w.dist, b + 6, (2 * d.max_pos - 1) * FD_HEAD_DIM);
+    UP(w.w_o, b + 7, H * H); UP(w.b_o, b + 8, H); UP(w.ln1_g, b + 9, H); UP(w.ln1_b, b + 10, H);
+    UP(w.w_i, b + 11, I * H); UP(w.b_i, b + 12, I);
+    UP(w.w_o2, b + 13, H * I); UP(w.b_o2, b + 14, H); UP(w.ln2_g, b + 15, H); UP(w.ln2_b, b + 16, H);
+  }
+  const int tb = FD_W_HEAD + d.layers * FD_W_PER_LAYER;
+  UP(h->w_d1, tb + 0, H * H); UP(h->b_d1, tb + 1, H); UP(h->hln_g, tb + 2, H); UP(h->hln_b, tb + 3, H);
+  UP(h->w_d2, tb + 4, F * H); UP(h->b_d2, tb + 5, F);
+#undef UP
+  if (!rc) rc = upload(h, &h->time_table, time_table, (size_t)d.timesteps * H);
+  h->coef.assign(coef, coef + (size_t)d.timesteps * 4);
+  // tensor-core operand planes of the weights (prepared once; cheap)
+  for (int l = 0; l < d.layers && !rc; ++l) {
+    LayerW& w = h->layers[l];
+    if (fd::tc_pack_weight(w.w_qkv, 3 * H, H, &w.tq) || fd::tc_pack_weight(w.w_o, H, H, &w.to) ||
+        fd::tc_pack_weight(w.w_i, I, H, &w.ti) || fd::tc_pack_weight(w.w_o2, H, I, &w.to2))
+      rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (!rc && fd::tc_pack_weight(h->w_d1, H, H, &h->td1)) rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed");
+  if (!rc) {
+    cudaFuncSetAttribute(fd::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)attn_smem_bytes(128, 128));
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(FD_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc) {
+    fd_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return FD_OK;
+}
+
+void fd_destroy(fd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  free_batch(h);
+  for (auto& w : h->layers) { fd::tc_free_weight(&w.tq); fd::tc_free_weight(&w.to); fd::tc_free_weight(&w.ti); fd::tc_free_weight(&w.to2); }
+  fd::tc_free_weight(&h->td1);
+  for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  delete h;
+}
+
+int32_t fd_set_schedule(fd_handle* h, int32_t timesteps, const float* time_table, const float* coef) {
+  if (!h || !time_table || !coef) return fail(FD_ERR_INVALID, "null argument");
+  if (timesteps < 1) return fail(FD_ERR_INVALID, "timesteps=%d", timesteps);
+  FD_CUDA(cudaSetDevice(h->device));
+  FD_CUDA(cudaDeviceSynchronize());  // no step may still be reading the old table
+  float* fresh = nullptr;
+  FD_CUDA(cudaMalloc(&fresh, sizeof(float) * (size_t)timesteps * h->d.hidden));
+  if (cudaMemcpy(fresh, time_table, sizeof(float) * (size_t)timesteps * h->d.hidden, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(fresh);
+    return fail(FD_ERR_CUDA, "time table upload failed");
+  }
+  for (auto& p : h->allocs)
+    if (p == h->time_table) p = fresh;
+  cudaFree(h->time_table);
+  h->time_table = fresh;
+  h->d.timesteps = timesteps;
+  h->coef.assign(coef, coef + (size_t)timesteps * 4);
+  return FD_OK;
+}
+
+int32_t fd_set_gemm_mode(fd_handle* h, int32_t gemm_mode) {
+  if (!h) return fail(FD_ERR_INVALID, "null handle");
+  if (gemm_mode < FD_GEMM_FP32_SIMT || gemm_mode > FD_GEMM_TC_1X) return fail(FD_ERR_INVALID, "bad gemm_mode");
+  h->gemm_mode = gemm_mode;
+  return FD_OK;
+}
+
+int64_t fd_launch_count(const fd_handle* h) { return h ? h->launches : 0; }
+
+int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* lengths,
+                     int32_t all_rows, const float* key_mask, void* stream) {
+  if (!h || !lengths) return fail(FD_ERR_INVALID, "null argument");
+  if (batch < 1 || n_pad < 1 || n_pad > h->d.max_pos)
+    return fail(FD_ERR_INVALID, "batch=%d n_pad=%d (max_pos=%d)", batch, n_pad, h->d.max_pos);
+  cudaStream_t st = (cudaStream_t)stream;
+  FD_CUDA(cudaSetDevice(h->device));
+  std::vector<int> row_start(batch), n_rows(batch), n_keys(batch);
+  long long rows = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (lengths[b] < 1 || lengths[b] > n_pad)
+      return fail(FD_ERR_INVALID, "lengths[%d]=%d outside [1, %d]", b, lengths[b], n_pad);
+    n_rows[b] = all_rows ? n_pad : lengths[b];
+    n_keys[b] = key_mask ? n_pad : lengths[b];
+    row_start[b] = (int)rows;
+    rows += n_rows[b];
+  }
+  const int rows_pad = (int)((rows + FD_ROW_TILE - 1) / FD_ROW_TILE * FD_ROW_TILE);
+  std::vector<int> row_src(rows_pad, 0);
+  for (int b = 0; b < batch; ++b)
+    for (int n = 0; n < n_rows[b]; ++n) row_src[row_start[b] + n] = b * n_pad + n;
+
+  const int Hd = h->d.hidden, I = h->d.intermediate;
+  if (batch > h->cap_batch || rows_pad > h->cap_rows || batch * n_pad > h->cap_bn) {
+    FD_CUDA(cudaStreamSynchronize(st));
+    free_batch(h);
+    const size_t r = (size_t)rows_pad;
+    FD_CUDA(cudaMalloc(&h->row_src, sizeof(int) * r));
+    FD_CUDA(cudaMalloc(&h->row_start, sizeof(int) * batch));
+    FD_CUDA(cudaMalloc(&h->n_rows, sizeof(int) * batch));
+    FD_CUDA(cudaMalloc(&h->n_keys, sizeof(int) * batch));
+    FD_CUDA(cudaMalloc(&h->key_bias, sizeof(float) * batch * n_pad));
+    FD_CUDA(cudaMalloc(&h->h, sizeof(float) * r * Hd));
+    FD_CUDA(cudaMalloc(&h->qkv, sizeof(float) * r * 3 * Hd));
+    FD_CUDA(cudaMalloc(&h->ctx, sizeof(float) * r * Hd));
+    FD_CUDA(cudaMalloc(&h->tmp, sizeof(float) * r * Hd));
+    FD_CUDA(cudaMalloc(&h->a, sizeof(float) * r * Hd));
+    FD_CUDA(cudaMalloc(&h->inter, sizeof(float) * r * I));
+    if (fd::tc_alloc_acts(&h->tc, rows_pad, Hd, I)) return fail(FD_ERR_CUDA, "tensor-core workspace allocation failed");
+    h->cap_batch = batch; h->cap_rows = rows_pad; h->cap_bn = batch * n_pad;
+    // rows beyond the last valid one are never written by the row-limited kernels: keep them 0
+    FD_CUDA(cudaMemsetAsync(h->h, 0, sizeof(float) * r * Hd, st));
+    FD_CUDA(cudaMemsetAsync(h->ctx, 0, sizeof(float) * r * Hd, st));
+    FD_CUDA(cudaMemsetAsync(h->a, 0, sizeof(float) * r * Hd, st));
+  }
+  h->batch = batch; h->n_pad = n_pad; h->rows = (int)rows; h->rows_pad = rows_pad; h->all_rows = all_rows;
+  FD_CUDA(cudaMemcpyAsync(h->row_src, row_src.data(), sizeof(int) * rows_pad, cudaMemcpyHostToDevice, st));
+  FD_CUDA(cudaMemcpyAsync(h->row_start, row_start.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+  FD_CUDA(cudaMemcpyAsync(h->n_rows, n_rows.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+  FD_CUDA(cudaMemcpyAsync(h->n_keys, n_keys.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+  h->has_key_bias = key_mask != nullptr;
+  if (key_mask) {
+    std::vector<float> bias((size_t)batch * n_pad);
+    for (size_t i = 0; i < bias.size(); ++i) bias[i] = (1.0f - key_mask[i]) * -10000.0f;  // modelling.py:452
+    FD_CUDA(cudaMemcpyAsync(h->key_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice, st));
+  }
+  // pageable-memory async copies have been staged by the time the call returns
+  return FD_OK;
+}
+
+int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, float* eps_out_dev,
+                   void* stream) {
+  if (!h || !x_dev || !temb_dev || !eps_out_dev) return fail(FD_ERR_INVALID, "null argument");
+  if (h->batch == 0) return fail(FD_ERR_STATE, "fd_set_batch has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  FD_CUDA(cudaSetDevice(h->device));
+  const int Hd = h->d.hidden;
+  FD_CUDA(cudaMemsetAsync(eps_out_dev, 0, sizeof(float) * h->batch * h->n_pad * h->d.n_features, st));
+  int rc;
+  fd::StepCoef none{};
+#define FD_FWD(V)                                                                                \
+  case V:                                                                                        \
+    rc = run_encoder<V>(h, x_dev, temb_dev, Hd, st);                                             \
+    if (!rc) launch_tail<V, false>(h, eps_out_dev, nullptr, nullptr, nullptr, none, 0u, st);     \
+    break;
+  switch (Hd / 32) {
+    FD_FWD(2) FD_FWD(4) FD_FWD(6) FD_FWD(8) FD_FWD(10) FD_FWD(12) FD_FWD(14) FD_FWD(16)
+    default: return fail(FD_ERR_UNSUPPORTED, "hidden=%d", Hd);
+  }
+#undef FD_FWD
+  if (rc) return rc;
+  return check_launch();
+}
+
+int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
+                          const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
+                          void* stream) {
+  if (!h || !x_dev || !wrap_mask) return fail(FD_ERR_INVALID, "null argument");
+  if (h->batch == 0) return fail(FD_ERR_STATE, "fd_set_batch has not been called");
+  if (t_lo < 0 || t_hi > h->d.timesteps || t_lo >= t_hi)
+    return fail(FD_ERR_INVALID, "need 0 <= t_lo < t_hi <= %d (got %d, %d)", h->d.timesteps, t_lo, t_hi);
+  if (!noise_dev && !(t_hi == 1 && t_lo == 0)) return fail(FD_ERR_INVALID, "noise_dev is required for steps with t > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  FD_CUDA(cudaSetDevice(h->device));
+  const int Hd = h->d.hidden, F = h->d.n_features;
+  uint32_t wrap_bits = 0;
+  for (int f = 0; f < F; ++f) wrap_bits |= (wrap_mask[f] ? 1u : 0u) << f;
+  const size_t slice = (size_t)h->batch * h->n_pad * F;
+  for (int t = t_hi - 1, k = 0; t >= t_lo; --t, ++k) {
+    const float* c = &h->coef[(size_t)t * 4];
+    fd::StepCoef coef{c[0], c[1], c[2], c[3], t > 0 ? 1 : 0};
+    const float* z = noise_dev ? noise_dev + (size_t)k * slice : nullptr;
+    float* hist = history_dev ? history_dev + (size_t)k * slice : nullptr;
+    const float* temb = h->time_table + (size_t)t * Hd;
+    int rc;
+#define FD_STEP(V)                                                                           \
+  case V:                                                                                    \
+    rc = run_encoder<V>(h, x_dev, temb, 0, st);                                              \
+    if (!rc) launch_tail<V, true>(h, nullptr, x_dev, z, hist, coef, wrap_bits, st);          \
+    break;
+    switch (Hd / 32) {
+      FD_STEP(2) FD_STEP(4) FD_STEP(6) FD_STEP(8) FD_STEP(10) FD_STEP(12) FD_STEP(14) FD_STEP(16)
+      default: return fail(FD_ERR_UNSUPPORTED, "hidden=%d", Hd);
+    }
+#undef FD_STEP
+    if (rc) return rc;
+  }
+  return check_launch();
+}
+
+int32_t fd_randn(float* dst_dev, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  if (!dst_dev || n < 0) return fail(FD_ERR_INVALID, "bad argument");
+  if (n == 0) return FD_OK;
+  fd::launch_philox_randn(dst_dev, n, seed, offset, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* lengths,
+                       const float* x0_host, int32_t t_start, const float* noise_host,
+                       uint64_t seed, const uint8_t* wrap_mask, int32_t full_history,
+                       float* out_host) {
+  if (!h || !lengths || !x0_host || !wrap_mask || !out_host) return fail(FD_ERR_INVALID, "null argument");
+  if (t_start < 1 || t_start > h->d.timesteps) return fail(FD_ERR_INVALID, "t_start=%d", t_start);
+  FD_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st;
+  FD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = fd_set_batch(h, batch, n_pad, lengths, 0, nullptr, st);
+  const size_t slice = (size_t)batch * n_pad * h->d.n_features;
+  const int chunk = t_start < 32 ? t_start : 32;
+  float *x = nullptr, *z = nullptr, *hist = nullptr;
+  auto cleanup = [&]() { cudaFree(x); cudaFree(z); cudaFree(hist); cudaStreamDestroy(st); };
+  if (!rc && cudaMalloc(&x, sizeof(float) * slice) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc x");
+  if (!rc && cudaMalloc(&z, sizeof(float) * slice * chunk) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc noise");
+  if (!rc && full_history && cudaMalloc(&hist, sizeof(float) * slice * chunk) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc history");
+  if (!rc && cudaMemcpyAsync(x, x0_host, sizeof(float) * slice, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "H2D x0");
+  if (!rc && hist) cudaMemsetAsync(hist, 0, sizeof(float) * slice * chunk, st);
+  int done = 0;
+  while (!rc && done < t_start) {
+    const int t_hi = t_start - done;
+    const int n = t_hi < chunk ? t_hi : chunk;
+    if (noise_host) {
+      if (cudaMemcpyAsync(z, noise_host + (size_t)done * slice, sizeof(float) * slice * n, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = fail(FD_ERR_CUDA, "H2D noise");
+    } else {
+      rc = fd_randn(z, (int64_t)(slice * n), seed, (uint64_t)done * slice, st);
+    }
+    if (!rc) rc = fd_p_sample_steps(h, x, t_hi, t_hi - n, z, hist, wrap_mask, st);
+    if (!rc && hist &&
+        cudaMemcpyAsync(out_host + (size_t)done * slice, hist, sizeof(float) * slice * n, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = fail(FD_ERR_CUDA, "D2H history");
+    done += n;
+  }
+  if (!rc && !full_history && cudaMemcpyAsync(out_host, x, sizeof(float) * slice, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    rc = fail(FD_ERR_CUDA, "D2H result");
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "sample_host: %s", cudaGetErrorString(cudaGetLastError()));
+  cleanup();
+  return rc;
+}
+
+int32_t fd_debug_gemm(int32_t gemm_mode, const float* a_dev, const float* w_dev,
+                      const float* bias_dev, float* c_dev, int32_t rows, int32_t n, int32_t k,
+                      void* stream) {
+  if (!a_dev || !w_dev || !c_dev) return fail(FD_ERR_INVALID, "null argument");
+  if (rows % FD_ROW_TILE || n % 64 || k % 64) return fail(FD_ERR_INVALID, "rows %% 128, n %% 64, k %% 64 must be 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* zero_bias = nullptr;
+  if (!bias_dev) {
+    FD_CUDA(cudaMalloc(&zero_bias, sizeof(float) * n));
+    FD_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * n, st));
+    bias_dev = zero_bias;
+  }
+  int rc = FD_OK;
+  if (gemm_mode == FD_GEMM_FP32_SIMT) {
+    launch_sgemm(nullptr, fd::EPI_BIAS, a_dev, w_dev, bias_dev, nullptr, c_dev, rows, n, k, st);
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    fd::TcWeight tw{};
+    fd::TcPlane ap{};
+    if (fd::tc_pack_weight(w_dev, n, k, &tw) || fd::tc_alloc_plane(&ap, rows, k)) {
+      rc = fail(FD_ERR_CUDA, "debug gemm: allocation failed");
+    } else {
+      fd::tc_split(a_dev, &ap, rows, k, gemm_mode, st);
+      int r = fd::tc_gemm(gemm_mode, fd::EPI_BIAS, &ap, &tw, bias_dev, nullptr, c_dev, nullptr, rows, n, k, sms, st);
+      if (r) rc = fail(FD_ERR_CUDA, "tensor-core GEMM launch failed (%d)", r);
+    }
+    cudaStreamSynchronize(st);
+    fd::tc_free_weight(&tw);
+    fd::tc_free_plane(&ap);
+  }
+  if (!rc) rc = check_launch();
+  if (zero_bias) { cudaStreamSynchronize(st); cudaFree(zero_bias); }
+  return rc;
+}
+
+int32_t fd_profile_begin(fd_handle* h) {
+  if (!h) return fail(FD_ERR_INVALID, "null handle");
+  FD_CUDA(cudaSetDevice(h->device));
+  FD_CUDA(cudaDeviceSynchronize());
+  h->prof_used = 0;
+  h->prof_cat.clear();
+  h->prof_on = true;
+  return FD_OK;
+}
+
+int32_t fd_profile_end(fd_handle* h, float* ms_out, int64_t* launches_out) {
+  if (!h || !ms_out || !launches_out) return fail(FD_ERR_INVALID, "null argument");
+  h->prof_on = false;
+  FD_CUDA(cudaSetDevice(h->device));
+  FD_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < CAT_COUNT; ++c) { ms_out[c] = 0.0f; launches_out[c] = 0; }
+  for (size_t i = 0; i < h->prof_cat.size(); ++i) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) {
+      ms_out[h->prof_cat[i]] += ms;
+      launches_out[h->prof_cat[i]] += 1;
+    }
+  }
+  return FD_OK;
+}
+
+int32_t fd_profile_num_categories(void) { return CAT_COUNT; }
+
+const char* fd_profile_category_name(int32_t i) { return (i >= 0 && i < CAT_COUNT) ? kCatNames[i] : ""; }
+
+int32_t fd_debug_tc_status(void) { return fd::tc_check_error(); }
+
+}  // extern "C"

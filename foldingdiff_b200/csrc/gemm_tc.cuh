@@ -1,0 +1,540 @@
+// Tensor-core projection GEMM for sm_100a:  C[M, N] = A[M, K] * W[N, K]^T (+bias)(+resid)(+GELU)
+//
+//   * tcgen05.mma (kind::f16, fp32 accumulate in TMEM), issued by one elected thread
+//   * operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, K-major)
+//   * warp-specialised persistent CTAs: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+//     warps 2..5 = epilogue (tcgen05.ld -> registers -> bias / residual / GELU -> global)
+//   * two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i + 1
+//
+// Precision.  The parity gate of this project is 1e-4 max-abs on fp32 angle tensors, which single
+// pass fp16/bf16/tf32 operands do not meet.  FD_GEMM_TC_3X therefore runs
+// an error-compensated split: every fp32 operand x is stored as two fp16 planes
+//     hi = fp16(x * 2^s),  lo = fp16(x * 2^s - hi)            (s = 0 for activations; for a weight
+//     matrix s is chosen so max|w| * 2^s is in [1024, 2048): keeps `lo` out of fp16 subnormals)
+// and the product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32 TMEM accumulator (the dropped
+// lo*lo term is ~2^-22 relative).  The epilogue multiplies by 2^-s (exact).  FD_GEMM_TC_1X issues
+// only the hi*hi pass (throughput mode, ~2^-11 relative operands).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"  // EPI_* and gelu_erf
+
+namespace fd {
+
+constexpr int TC_BM = 128;         // rows per tile (one UMMA M)
+constexpr int TC_BK = 64;          // fp16 elements per 128-byte swizzle row
+constexpr int TC_UMMA_K = 16;      // K of one tcgen05.mma.kind::f16
+constexpr int TC_THREADS = 192;    // 6 warps
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+struct TcPlane {         // fp16 hi / lo planes of an activation matrix [rows, k]
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int rows = 0, k = 0;
+  CUtensorMap map_hi, map_lo;  // box {64, 128}
+};
+struct TcWeight {        // fp16 hi / lo planes of a weight matrix [n, k], scaled by 2^shift
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int n = 0, k = 0, bn = 0;
+  float inv_scale = 1.0f;      // 2^-shift
+  CUtensorMap map_hi, map_lo;  // box {64, bn}
+};
+struct TcActs {
+  TcPlane h, ctx, a, inter;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline must end the kernel with an error flag, never hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) return false;  // ~2 s
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes
+// apart (SBO), LBO is unused for swizzled K-major layouts (encoded 1), descriptor version 1
+// (sm_100), layout type 2 = SWIZZLE_128B.  Fields are in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // version = 1
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = bn.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int bn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int NPASS>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;                     // 16 KB per plane
+  static constexpr int W_BYTES = BN * TC_BK * 2;                        // BN * 128 B per plane
+  static constexpr int PLANES = NPASS == 1 ? 1 : 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "tile too large");
+  static_assert(2 * BN <= (int)TC_TMEM_COLS, "two accumulators must fit TMEM");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+};
+
+template <int BN, int NPASS, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const float* __restrict__ bias, const float* __restrict__ resid, float* __restrict__ C,
+               __half* __restrict__ c_hi, __half* __restrict__ c_lo, int M, int N, int K,
+               float out_scale, int* __restrict__ err_flag) {
+  using Cfg = TcCfg<BN, NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                          // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + Cfg::STAGES;           // [STAGES]   MMA -> TMA
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;    // [2]        MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / BN, m_blocks = M / TC_BM;
+  const int n_tiles = n_blocks * m_blocks, k_blocks = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_w_hi);
+    if (NPASS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_lo); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int m0 = (tile / n_blocks) * TC_BM, n0 = (tile % n_blocks) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          if (!mbar_wait(&empty[stage], phase ^ 1)) { atomicExch(err_flag, 101); ok = false; break; }
+          uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(s, &map_a_hi, &full[stage], kb * TC_BK, m0);
+          tma_load_2d(s + Cfg::PLANES * Cfg::A_BYTES, &map_w_hi, &full[stage], kb * TC_BK, n0);
+          if (NPASS > 1) {
+            tma_load_2d(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
+            tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, &full[stage], kb * TC_BK, n0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(&acc_empty[acc], acc_phase ^ 1)) { atomicExch(err_flag, 102); break; }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          if (!mbar_wait(&full[stage], phase)) { atomicExch(err_flag, 103); ok = false; break; }
+          tc_fence_after();
+          const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_hi = s, a_lo = s + Cfg::A_BYTES;
+          const uint32_t w_hi = s + Cfg::PLANES * Cfg::A_BYTES, w_lo = w_hi + Cfg::W_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint32_t koff = k * TC_UMMA_K * 2;  // bytes inside the 128-byte swizzle row
+            const uint64_t da_hi = umma_desc_sw128(a_hi + koff), dw_hi = umma_desc_sw128(w_hi + koff);
+            umma_f16(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NPASS > 1) {
+              const uint64_t da_lo = umma_desc_sw128(a_lo + koff), dw_lo = umma_desc_sw128(w_lo + koff);
+              umma_f16(d_tmem, da_hi, dw_lo, idesc, 1u);
+              umma_f16(d_tmem, da_lo, dw_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above retire
+          if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_blocks) * TC_BM, n0 = (tile % n_blocks) * BN;
+      if (!mbar_wait(&acc_full[acc], acc_phase)) { if (lane == 0) atomicExch(err_flag, 104); break; }
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        const size_t off = (size_t)row * N + n0 + c0;
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+          o[j] = fmaf(__uint_as_float(v[j]), out_scale, b4.x);
+          o[j + 1] = fmaf(__uint_as_float(v[j + 1]), out_scale, b4.y);
+          o[j + 2] = fmaf(__uint_as_float(v[j + 2]), out_scale, b4.z);
+          o[j + 3] = fmaf(__uint_as_float(v[j + 3]), out_scale, b4.w);
+          if (EPI == EPI_BIAS_RESID) {
+            const float4 r4 = *reinterpret_cast<const float4*>(resid + off + j);
+            o[j] += r4.x; o[j + 1] += r4.y; o[j + 2] += r4.z; o[j + 3] += r4.w;
+          }
+          if (EPI == EPI_BIAS_GELU) {
+            o[j] = gelu_erf(o[j]); o[j + 1] = gelu_erf(o[j + 1]);
+            o[j + 2] = gelu_erf(o[j + 2]); o[j + 3] = gelu_erf(o[j + 3]);
+          }
+        }
+        if (C) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(C + off + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+        if (c_hi) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __half h0 = __float2half_rn(o[j + 2 * q]), h1 = __float2half_rn(o[j + 2 * q + 1]);
+              const __half l0 = __float2half_rn(o[j + 2 * q] - __half2float(h0));
+              const __half l1 = __float2half_rn(o[j + 2 * q + 1] - __half2float(h1));
+              ph[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              pl[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(c_hi + off + j) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            if (c_lo) *reinterpret_cast<uint4*>(c_lo + off + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);  // 128 arrivals release the accumulator to the MMA warp
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_split_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                __half* __restrict__ lo, size_t n4, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2half_rn(x[j]);
+      l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+    }
+    uint2 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    reinterpret_cast<uint2*>(hi)[i] = ph;
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = pl;
+  }
+}
+
+__global__ void tc_absmax_kernel(const float* __restrict__ src, size_t n, unsigned int* out_bits) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(src[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+
+inline tc_encode_fn tc_encoder() {
+  static tc_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tc_encode_fn>(p);
+  }
+  return fn;
+}
+
+// [rows, k] fp16 row-major -> TMA map with box {64 (k), box_rows}, 128-byte swizzle.
+inline int tc_make_map(CUtensorMap* map, const __half* base, int rows, int k, int box_rows) {
+  tc_encode_fn enc = tc_encoder();
+  if (!enc) return 1;
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)k * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+inline int tc_pick_bn(int n) {
+  if (n % 192 == 0) return 192;
+  if (n % 128 == 0) return 128;
+  return 64;
+}
+
+inline int tc_alloc_plane(TcPlane* p, int rows, int k) {
+  p->rows = rows; p->k = k;
+  if (cudaMalloc(&p->hi, sizeof(__half) * (size_t)rows * k) != cudaSuccess) return 1;
+  if (cudaMalloc(&p->lo, sizeof(__half) * (size_t)rows * k) != cudaSuccess) return 1;
+  cudaMemset(p->hi, 0, sizeof(__half) * (size_t)rows * k);
+  cudaMemset(p->lo, 0, sizeof(__half) * (size_t)rows * k);
+  if (tc_make_map(&p->map_hi, p->hi, rows, k, TC_BM)) return 2;
+  if (tc_make_map(&p->map_lo, p->lo, rows, k, TC_BM)) return 2;
+  return 0;
+}
+inline void tc_free_plane(TcPlane* p) {
+  cudaFree(p->hi); cudaFree(p->lo);
+  p->hi = p->lo = nullptr;
+}
+inline int tc_alloc_acts(TcActs* a, int rows_pad, int hidden, int inter) {
+  if (tc_alloc_plane(&a->h, rows_pad, hidden)) return 1;
+  if (tc_alloc_plane(&a->ctx, rows_pad, hidden)) return 1;
+  if (tc_alloc_plane(&a->a, rows_pad, hidden)) return 1;
+  if (tc_alloc_plane(&a->inter, rows_pad, inter)) return 1;
+  return 0;
+}
+inline void tc_free_acts(TcActs* a) {
+  tc_free_plane(&a->h); tc_free_plane(&a->ctx); tc_free_plane(&a->a); tc_free_plane(&a->inter);
+}
+
+// fp32 [n, k] device weight -> scaled fp16 hi / lo planes + TMA maps.  Synchronous (create time).
+inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out) {
+  out->n = n; out->k = k; out->bn = tc_pick_bn(n);
+  const size_t cnt = (size_t)n * k;
+  unsigned int* bits = nullptr;
+  if (cudaMalloc(&bits, sizeof(unsigned int)) != cudaSuccess) return 1;
+  cudaMemset(bits, 0, sizeof(unsigned int));
+  tc_absmax_kernel<<<64, 256>>>(w_dev, cnt, bits);
+  unsigned int hb = 0;
+  if (cudaMemcpy(&hb, bits, sizeof(hb), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(bits); return 1; }
+  cudaFree(bits);
+  float amax;
+  memcpy(&amax, &hb, sizeof(amax));
+  int shift = 0;
+  if (amax > 0.0f && amax < 3.0e38f) {
+    int e;
+    frexpf(amax, &e);       // amax = f * 2^e, f in [0.5, 1)
+    shift = 11 - e;         // amax * 2^shift in [1024, 2048)
+    if (shift > 24) shift = 24;
+    if (shift < -4) shift = -4;
+  }
+  out->inv_scale = ldexpf(1.0f, -shift);
+  if (cudaMalloc(&out->hi, sizeof(__half) * cnt) != cudaSuccess) return 1;
+  if (cudaMalloc(&out->lo, sizeof(__half) * cnt) != cudaSuccess) return 1;
+  tc_split_kernel<<<256, 256>>>(w_dev, out->hi, out->lo, cnt / 4, ldexpf(1.0f, shift));
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (tc_make_map(&out->map_hi, out->hi, n, k, out->bn)) return 2;
+  if (tc_make_map(&out->map_lo, out->lo, n, k, out->bn)) return 2;
+  return 0;
+}
+inline void tc_free_weight(TcWeight* w) {
+  cudaFree(w->hi); cudaFree(w->lo);
+  w->hi = w->lo = nullptr;
+}
+
+// fp32 activations -> fp16 hi (/ lo) planes.
+inline void tc_split(const float* src, TcPlane* dst, int rows, int cols, int mode, cudaStream_t st) {
+  const size_t n4 = (size_t)rows * cols / 4;
+  const int blocks = (int)((n4 + 255) / 256 > 148 * 8 ? 148 * 8 : (n4 + 255) / 256);
+  tc_split_kernel<<<blocks, 256, 0, st>>>(src, dst->hi, mode == 1 /*FD_GEMM_TC_3X*/ ? dst->lo : nullptr, n4, 1.0f);
+}
+
+inline int* tc_err_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+// Reads (and clears) the device-side pipeline error flag; synchronises the device.
+inline int tc_check_error() {
+  int* f = tc_err_flag();
+  int v = 0;
+  if (!f) return -1;
+  if (cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  if (v) cudaMemset(f, 0, sizeof(int));
+  return v;
+}
+
+template <int BN, int NPASS, int EPI>
+int tc_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
+              TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+  using Cfg = TcCfg<BN, NPASS>;
+  static bool configured = false;
+  auto kern = tc_gemm_kernel<BN, NPASS, EPI>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
+    configured = true;
+  }
+  int* err = tc_err_flag();
+  if (!err) return 11;
+  const int tiles = (M / TC_BM) * (N / BN);
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a->map_hi, a->map_lo, w->map_hi, w->map_lo, bias, resid, C,
+                                                  c_tc ? c_tc->hi : nullptr,
+                                                  (c_tc && NPASS > 1) ? c_tc->lo : nullptr, M, N, K,
+                                                  w->inv_scale, err);
+  return cudaGetLastError() == cudaSuccess ? 0 : 12;
+}
+
+template <int BN, int NPASS>
+int tc_dispatch_epi(int epi, const TcPlane* a, const TcWeight* w, const float* bias, const float* resid,
+                    float* C, TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return tc_launch<BN, NPASS, EPI_BIAS>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    case EPI_BIAS_GELU: return tc_launch<BN, NPASS, EPI_BIAS_GELU>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    default: return tc_launch<BN, NPASS, EPI_BIAS_RESID>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  }
+}
+
+// mode: 1 = FD_GEMM_TC_3X, 2 = FD_GEMM_TC_1X
+inline int tc_gemm(int mode, int epi, const TcPlane* a, const TcWeight* w, const float* bias,
+                   const float* resid, float* C, TcPlane* c_tc, int M, int N, int K, int sm_count,
+                   cudaStream_t st) {
+  if (!a || !w || M % TC_BM || K % TC_BK || N % w->bn || a->k != K || w->k != K || w->n != N) return 20;
+  const bool three = mode == 1;
+  switch (w->bn) {
+    case 192:
+      return three ? tc_dispatch_epi<192, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
+                   : tc_dispatch_epi<192, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    case 128:
+      return three ? tc_dispatch_epi<128, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
+                   : tc_dispatch_epi<128, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    case 64:
+      return three ? tc_dispatch_epi<64, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
+                   : tc_dispatch_epi<64, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  }
+  return 21;
+}
+
+}  // namespace fd

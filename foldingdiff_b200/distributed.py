@@ -1,0 +1,71 @@
+"""
+Chain sharding across the GPUs of one box.
+
+Independent chains are the only parallel axis of the sampler: there is no exchange inside the
+T-step loop.  Each rank (one process per GPU, torch.distributed over NCCL) holds a replica of the
+weights (58 MB), runs the native loop on its share of the chains, and ONE all-gather of the finished
+`(B_local, N, F)` angle tensors (1.5 MB per 512 chains) restores the reference's output order.
+The reference itself samples on a single device (bin/sample.py:286,341-343).
+
+Chains are dealt round-robin (`chain i -> rank i % world`) because `sampling.sample` emits lengths in
+ascending order (reference sampling.py:168-175): every rank then sees the same length mix, i.e. equal
+work per rank.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    return list(range(rank, n_items, world))
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sharded_final_angles(run_fn: Callable[[List[int], torch.Tensor], torch.Tensor],
+                         lengths: Sequence[int], noise: torch.Tensor, group=None,
+                         gather_device: Optional[torch.device] = None) -> torch.Tensor:
+    """
+    Run `run_fn(local_lengths, local_noise) -> (B_local, N, F)` final angles on this rank's share of
+    the batch and return the full `(B, N, F)` tensor (CPU) in the original chain order on EVERY rank.
+    `noise` is the full-batch initial noise, identical on all ranks (drawn from the same seeded CPU
+    generator, which keeps the sharded run bit-identical to the single-device one at t = T).
+    """
+    rank, world = _world(group)
+    B = len(lengths)
+    mine = shard_indices(B, rank, world)
+    local = run_fn([int(lengths[i]) for i in mine], noise[mine])
+    if world == 1:
+        return local.cpu()
+    per_rank = (B + world - 1) // world
+    dev = gather_device if gather_device is not None else local.device
+    send = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=torch.float32, device=dev)
+    send[: len(mine)] = local.to(dev)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)  # the one collective of the whole job
+    out = torch.empty((B,) + tuple(local.shape[1:]), dtype=torch.float32)
+    for r in range(world):
+        idx = shard_indices(B, r, world)
+        out[idx] = recv[r][: len(idx)].cpu()
+    return out
+
+
+def sample_final_sharded(model, lengths: Sequence[int], noise: torch.Tensor, timesteps: int,
+                         betas: torch.Tensor, is_angle, group=None) -> torch.Tensor:
+    """Multi-GPU `p_sample_loop(..., history="final")[-1]`: (B, N, F) final angles on every rank."""
+    from . import sampling
+
+    def run(local_lengths, local_noise):
+        dev = next(model.parameters()).device
+        out = sampling.p_sample_loop(model, local_lengths, local_noise, timesteps, betas, is_angle=is_angle,
+                                     disable_pbar=True, history="final")
+        return out[-1].to(dev)
+
+    return sharded_final_angles(run, lengths, noise, group=group)

@@ -1,0 +1,219 @@
+"""
+Reverse-diffusion sampling: the reference's `sampling` surface on the native CUDA step.
+
+Same call signatures and return types as /root/reference/foldingdiff/sampling.py:
+  p_sample (:28), p_sample_loop (:79), sample (:135), sample_simple (:227),
+  get_reconstruction_error (:288, denoising loop only - scoring needs TMalign/biotite).
+
+How the loop is executed differs (this is the hot path the project replaces):
+  * one `fd_p_sample_steps` call runs a whole window of reverse steps on the device: the
+    noise-predictor forward, the posterior update, the per-column mod-2pi wrap and the history
+    write are kernels enqueued back to back - no per-step `.item()` sync, no B-iteration mask loop,
+    no `compute_alphas` per step, no per-step `img.cpu()` (reference sampling.py:42-58, :131);
+  * only the valid residues of each chain are computed (the reference computes padded rows and
+    throws them away, sampling.py:201-203).  Padded positions of returned tensors are 0 in the
+    history and left at their input value in `p_sample`;
+  * the per-step normals are still drawn with torch's generator for the model's device, one
+    `(B, N, F)` draw per step with t > 0 in the reference's order (sampling.py:73), so a seeded run
+    consumes RNG state exactly like the reference on the same device.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import pandas as pd
+import torch
+from torch import nn
+
+from . import datasets as dsets
+from . import modelling, utils
+
+# reverse steps handed to the device per native call (bounds the pre-drawn noise buffer)
+STEP_WINDOW = int(os.environ.get("FOLDINGDIFF_B200_STEP_WINDOW", "50"))
+
+
+def _engine_for(model: nn.Module):
+    if not hasattr(model, "native_engine"):
+        raise TypeError(
+            f"{type(model).__name__} is not a foldingdiff_b200 model: the native sampler runs the "
+            "built-in noise predictor only (load one with BertForDiffusionBase.from_dir)")
+    return model.native_engine()
+
+
+def _draw_normal(out: torch.Tensor) -> None:
+    """Fill `out` with standard normals from torch's generator for its device: the same stream
+    consumption as the reference's `torch.randn_like(x)` (sampling.py:73).  Tests patch this hook to
+    feed the CPU oracle's draws to the device."""
+    torch.randn(out.shape, device=out.device, dtype=out.dtype, out=out)
+
+
+def _wrap_mask(is_angle: Union[bool, Sequence[bool]], n_features: int) -> List[bool]:
+    if isinstance(is_angle, bool):
+        return [is_angle] * n_features
+    assert len(is_angle) == n_features
+    return [bool(a) for a in is_angle]
+
+
+@torch.no_grad()
+def p_sample(model: nn.Module, x: torch.Tensor, t: torch.Tensor, seq_lens: Sequence[int],
+             t_index: torch.Tensor, betas: torch.Tensor) -> torch.Tensor:
+    """One posterior step x_t -> x_{t-1} (no wrap; see p_sample_loop).  All entries of `t` must agree."""
+    t_unique = torch.unique(t)
+    assert len(t_unique) == 1, f"Got multiple values for t: {t_unique}"
+    ti = int(t_unique.item())
+    eng = _engine_for(model)
+    eng.set_schedule(betas)
+    lens = [int(l) for l in (seq_lens.reshape(-1).tolist() if torch.is_tensor(seq_lens) else seq_lens)]
+    eng.set_batch(lens, x.shape[1])
+    out = x.detach().to(torch.float32).contiguous().clone()
+    z = None
+    if ti > 0:
+        z = torch.empty_like(out)
+        _draw_normal(z)
+    eng.p_sample_steps(out, ti + 1, ti, z, None, [False] * x.shape[-1])
+    return out
+
+
+def _run_steps(eng, x: torch.Tensor, t_start: int, wrap: Sequence[bool],
+               history: Optional[torch.Tensor]) -> None:
+    """Steps t = t_start-1 .. 0 in windows; draws each step's normals like `torch.randn_like(x)`."""
+    B, N, F = x.shape
+    done = 0
+    while done < t_start:
+        t_hi = t_start - done
+        n = min(STEP_WINDOW, t_hi)
+        z = torch.empty((n, B, N, F), device=x.device, dtype=torch.float32)
+        for k in range(n):
+            if t_hi - 1 - k > 0:  # the reference draws nothing at t == 0
+                _draw_normal(z[k])
+        eng.p_sample_steps(x, t_hi, t_hi - n, z, None if history is None else history[done:done + n], wrap)
+        done += n
+
+
+@torch.no_grad()
+def p_sample_loop(model: nn.Module, lengths: Sequence[int], noise: torch.Tensor, timesteps: int,
+                  betas: torch.Tensor, is_angle: Union[bool, List[bool]] = [False, True, True, True],
+                  disable_pbar: bool = False, history: str = "full") -> torch.Tensor:
+    """
+    Returns a CPU tensor of shape (timesteps, batch_size, seq_len, n_ft): entry k is the state after
+    the k-th reverse step, entry -1 is x_0.  `history="final"` (extension) returns only that last
+    entry, shape (1, batch, seq_len, n_ft), so `result[-1]` means the same thing either way.
+    """
+    device = next(model.parameters()).device
+    eng = _engine_for(model)
+    eng.set_schedule(betas, timesteps)
+    x = noise.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+    B, N, F = x.shape
+    logging.info(f"Starting from noise {tuple(noise.shape)} with angularity {is_angle} using {device}")
+    eng.set_batch([int(l) for l in lengths], N)
+    wrap = _wrap_mask(is_angle, F)
+    if history == "full":
+        hist = torch.zeros((timesteps, B, N, F), device=device, dtype=torch.float32)
+        _run_steps(eng, x, timesteps, wrap, hist)
+        return hist.cpu()
+    assert history == "final", history
+    _run_steps(eng, x, timesteps, wrap, None)
+    valid = torch.arange(N, device=device)[None, :] < torch.as_tensor(list(lengths), device=device)[:, None]
+    return (x * valid[..., None]).unsqueeze(0).cpu()
+
+
+def sample(model: nn.Module, train_dset, n: int = 10, sweep_lengths: Optional[Tuple[int, int]] = (50, 128),
+           batch_size: int = 512, feature_key: str = "angles", disable_pbar: bool = False,
+           trim_to_length: bool = True, history: str = "full") -> List[np.ndarray]:
+    """
+    Sample `n` chains per length in [sweep_min, sweep_max) (upper bound exclusive, like the
+    reference), or `n` chains with lengths from `train_dset.sample_length()` when
+    `sweep_lengths` is None.  Returns arrays of shape (timesteps, seq_len, n_ft) in length order
+    ((1, seq_len, n_ft) with history="final").  `train_dset` needs: sample_noise, timesteps,
+    alpha_beta_terms, feature_is_angular, pad (and optionally dset.get_masked_means()).
+    """
+    if sweep_lengths is not None:
+        lo, hi = sweep_lengths
+        if not lo < hi:
+            raise ValueError(f"Minimum length {lo} must be less than maximum {hi}")
+        lengths = [l for l in range(lo, hi) for _ in range(n)]
+    else:
+        lengths = [train_dset.sample_length() for _ in range(n)]
+    logging.info(f"Sampling {len(lengths)} items in batches of size {batch_size}")
+    out: List[np.ndarray] = []
+    for chunk in utils.seq_to_groups(lengths, batch_size):
+        noise = train_dset.sample_noise(
+            torch.zeros((len(chunk), train_dset.pad, model.n_inputs), dtype=torch.float32))
+        if trim_to_length:
+            noise = noise[:, : max(chunk), :]
+        sampled = p_sample_loop(model=model, lengths=chunk, noise=noise, timesteps=train_dset.timesteps,
+                                betas=train_dset.alpha_beta_terms["betas"],
+                                is_angle=train_dset.feature_is_angular[feature_key],
+                                disable_pbar=disable_pbar, history=history)
+        out.extend(sampled[:, i, :l, :].numpy() for i, l in enumerate(chunk))
+    inner = getattr(train_dset, "dset", None)
+    if inner is not None and hasattr(inner, "get_masked_means") and inner.get_masked_means() is not None:
+        means = inner.get_masked_means()
+        logging.info(f"Shifting predicted values by original offset: {means}")
+        out = [s + means for s in out]
+        angular_idx = np.where(train_dset.feature_is_angular[feature_key])[0]
+        for s in out:  # the shift may cross the circle boundary
+            s[..., angular_idx] = utils.modulo_with_wrapped_range(s[..., angular_idx], -np.pi, np.pi)
+    return out
+
+
+def sample_simple(model_dir: str, n: int = 10, sweep_lengths: Tuple[int, int] = (50, 128)) -> List[pd.DataFrame]:
+    """Load a model directory and sample; one DataFrame of final angles per chain."""
+    assert os.path.isdir(model_dir), f"{model_dir} is not a directory (hub ids need network access)"
+    with open(os.path.join(model_dir, "training_args.json")) as f:
+        targs = json.load(f)
+    model = modelling.BertForDiffusionBase.from_dir(model_dir).to("cuda:0")
+    dummy = dsets.AnglesEmptyDataset.from_dir(model_dir)
+    noised = dsets.NoisedAnglesDataset(dset=dummy, dset_key="angles", timesteps=targs["timesteps"],
+                                       exhaustive_t=False, beta_schedule=targs["variance_schedule"],
+                                       nonangular_variance=1.0, angular_variance=targs["variance_scale"])
+    sampled = sample(model, noised, n=n, sweep_lengths=sweep_lengths, disable_pbar=True, history="final")
+    return [pd.DataFrame(s[-1], columns=noised.feature_names["angles"]) for s in sampled]
+
+
+@torch.no_grad()
+def denoise_from(model: nn.Module, corrupted: torch.Tensor, lengths: Sequence[int], noise_timesteps: int,
+                 betas: torch.Tensor) -> torch.Tensor:
+    """
+    The partial-denoise loop of get_reconstruction_error (reference sampling.py:311-330): start from
+    x_t at t = noise_timesteps, run t = noise_timesteps-1 .. 0, wrapping EVERY column with the
+    default +-pi range after each step (the reference calls modulo_with_wrapped_range(img) there,
+    not the per-feature wrap of p_sample_loop).  Returns the (B, N, F) result on `corrupted.device`.
+    """
+    device = next(model.parameters()).device
+    eng = _engine_for(model)
+    eng.set_schedule(betas)
+    x = corrupted.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+    eng.set_batch([int(l) for l in lengths], x.shape[1])
+    _run_steps(eng, x, noise_timesteps, [True] * x.shape[-1], None)
+    return x
+
+
+@torch.no_grad()
+def get_reconstruction_error(model: nn.Module, dset, noise_timesteps: int = 250, bs: int = 512,
+                             score_fn=None):
+    """
+    Noise every item of `dset` to t = noise_timesteps, denoise it back, and return
+    (reconstructed, truth) lists of per-chain DataFrames - plus `score_fn(recon, truth, filename)`
+    results when a scorer is given.  The reference scores with NeRF + the TMalign binary
+    (sampling.py:267-284, 343-356), which this image does not have; that tail is out of scope.
+    """
+    model.eval()
+    cols = dset.feature_names["angles"]
+    recon, truth, files = [], [], []
+    for idx_batch in utils.seq_to_groups(list(range(len(dset))), bs):
+        items = [dset.__getitem__(i, use_t_val=noise_timesteps) for i in idx_batch]
+        corrupted = torch.stack([it["corrupted"] for it in items])
+        lengths = [int(it["lengths"]) for it in items]
+        img = denoise_from(model, corrupted, lengths, noise_timesteps, dset.alpha_beta_terms["betas"]).cpu()
+        for j, (it, i, l) in enumerate(zip(items, idx_batch, lengths)):
+            recon.append(pd.DataFrame(img[j, :l].numpy(), columns=cols))
+            truth.append(pd.DataFrame(it["angles"][:l].numpy(), columns=cols))
+            files.append(dset.filenames[i] if hasattr(dset, "filenames") else None)
+    if score_fn is None:
+        return recon, truth
+    return np.array([score_fn(r, t, f) for r, t, f in zip(recon, truth, files)])
