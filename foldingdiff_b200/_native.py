@@ -60,6 +60,8 @@ SIGNATURES = {
     "fd_profile_category_name": (C.c_char_p, [C.c_int32]),
     "fd_debug_gemm": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "fd_debug_attention": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fd_debug_tc_status": (C.c_int32, []),
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/foldingdiff_b200.h"
+#include "attention_mma.cuh"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
@@ -39,6 +40,7 @@ int fail(int code, const char* fmt, ...) {
 struct LayerW {
   float *w_qkv, *b_qkv, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
   fd::TcWeight tq, to, ti, to2;  // tensor-core operand planes (hi / lo) of the four projections
+  __half *e_hi = nullptr, *e_lo = nullptr;  // distance embedding as fp16 hi / lo, padded to 256 rows
 };
 
 }  // namespace
@@ -124,21 +126,25 @@ void free_batch(fd_handle* h) {
 }
 
 template <int VPL>
-void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
+void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stride, fd::TcPlane* planes,
+                  cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_EMBED, st);
   fd::embed_kernel<VPL><<<blocks, 256, 0, st>>>(x, H->row_src, H->rows, H->n_pad, H->d.n_features,
                                                 H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps,
-                                                temb, temb_stride, H->h);
+                                                temb, temb_stride, H->h, planes ? planes->hi : nullptr,
+                                                (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : nullptr);
   H->launches++;
 }
 
 template <int VPL>
 void launch_ln(fd_handle* H, const float* in, const float* g, const float* b, float* out,
-               cudaStream_t st) {
+               fd::TcPlane* planes, cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_LN, st);
-  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, H->rows, g, b, H->d.ln_eps, out);
+  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, H->rows, g, b, H->d.ln_eps, out,
+                                                    planes ? planes->hi : nullptr,
+                                                    (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : nullptr);
   H->launches++;
 }
 
@@ -172,6 +178,24 @@ void launch_attention(fd_handle* H, const float* dist, cudaStream_t st) {
   H->launches++;
 }
 
+// tensor-core attention on the fp16 hi / lo planes (tc modes): qkv planes -> ctx planes
+void launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
+  const int items = H->batch * H->d.heads;
+  const int grid = items < H->sm_count ? items : H->sm_count;
+  const size_t smem = fd::att_smem_bytes();
+  const float* bias = H->has_key_bias ? H->key_bias : nullptr;
+  ProfScope ps(H, CAT_ATTN, st);
+  if (H->gemm_mode == FD_GEMM_TC_3X)
+    fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, smem, st>>>(
+        H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
+        H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
+  else
+    fd::attention_mma_kernel<false><<<grid, fd::ATT_WARPS * 32, smem, st>>>(
+        H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
+        H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
+  H->launches++;
+}
+
 template <int VPL, bool SAMPLE>
 void launch_tail(fd_handle* H, float* eps_out, float* x, const float* z, float* hist,
                  fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st) {
@@ -202,32 +226,32 @@ int project(fd_handle* H, int cat, int epi, const float* A, const float* W, cons
 }
 
 // The noise-predictor forward on the current batch: leaves gelu(dense1(h_L)) in H->tmp.
+// fp32 mode: every tensor fp32, CUDA-core kernels.  tc modes: the residual stream (h, a, tmp) stays
+// fp32; GEMM operands travel as fp16 hi / lo planes written by the producing kernel's epilogue
+// (embed / LayerNorm / QKV GEMM / attention / FFN1 GEMM) - no separate conversion passes.
 template <int VPL>
 int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
   const int Hd = H->d.hidden, I = H->d.intermediate;
   const bool tcm = H->gemm_mode != FD_GEMM_FP32_SIMT;
-  launch_embed<VPL>(H, x, temb, temb_stride, st);
-  if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->h, &H->tc.h, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+  launch_embed<VPL>(H, x, temb, temb_stride, tcm ? &H->tc.h : nullptr, st);
   for (int l = 0; l < H->d.layers; ++l) {
     LayerW& w = H->layers[l];
-    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, w.b_qkv, nullptr, H->qkv, 3 * Hd, Hd,
-                     &H->tc.h, nullptr, st);
+    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, w.b_qkv, nullptr, tcm ? nullptr : H->qkv,
+                     3 * Hd, Hd, &H->tc.h, tcm ? &H->tc.qkv : nullptr, st);
     if (rc) return rc;
-    launch_attention(H, w.dist, st);
-    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->ctx, &H->tc.ctx, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+    if (tcm) launch_attention_mma(H, w, st);
+    else launch_attention(H, w.dist, st);
     rc = project(H, CAT_GEMM_OUT, fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp, Hd, Hd,
                  &H->tc.ctx, nullptr, st);
     if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, w.ln1_g, w.ln1_b, H->a, st);
-    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->a, &H->tc.a, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
-    rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, H->inter, I, Hd,
-                 &H->tc.a, &H->tc.inter, st);
+    launch_ln<VPL>(H, H->tmp, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
+    rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, tcm ? nullptr : H->inter,
+                 I, Hd, &H->tc.a, tcm ? &H->tc.inter : nullptr, st);
     if (rc) return rc;
     rc = project(H, CAT_GEMM_FFN2, fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a, H->tmp, Hd, I,
                  &H->tc.inter, nullptr, st);
     if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, w.ln2_g, w.ln2_b, H->h, st);
-    if (tcm) { ProfScope ps(H, CAT_SPLIT, st); fd::tc_split(H->h, &H->tc.h, H->rows_pad, Hd, H->gemm_mode, st); H->launches++; }
+    launch_ln<VPL>(H, H->tmp, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
   }
   return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, &H->td1, H->b_d1, nullptr, H->tmp, Hd, Hd,
                  &H->tc.h, nullptr, st);
@@ -248,7 +272,7 @@ int32_t fd_num_weights(int32_t layers) { return FD_W_HEAD + FD_W_PER_LAYER * lay
 int32_t fd_abi_version(void) { return FD_ABI_VERSION; }
 
 const char* fd_build_info(void) {
-  return "foldingdiff_b200 sm_100a; gemm: fp32-simt, tcgen05-3x, tcgen05-1x; attention: fp32-simt";
+  return "foldingdiff_b200 sm_100a; gemm: fp32-simt, tcgen05-3x, tcgen05-1x; attention: fp32-simt, mma.sync-3x";
 }
 
 const char* fd_last_error(void) { return g_err.c_str(); }
@@ -269,6 +293,8 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
   if (n_weights != fd_num_weights(d.layers))
     return fail(FD_ERR_INVALID, "expected %d weight tensors, got %d", fd_num_weights(d.layers), n_weights);
   if (gemm_mode < FD_GEMM_FP32_SIMT || gemm_mode > FD_GEMM_TC_1X) return fail(FD_ERR_INVALID, "bad gemm_mode");
+  if (gemm_mode != FD_GEMM_FP32_SIMT && d.max_pos != 128)
+    return fail(FD_ERR_UNSUPPORTED, "the tensor-core path is specialised for max_position_embeddings = 128 (got %d); use FD_GEMM_FP32_SIMT", d.max_pos);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(FD_ERR_CUDA, "no CUDA device visible: foldingdiff_b200 has no CPU fallback");
@@ -319,9 +345,25 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
       rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (!rc && fd::tc_pack_weight(h->w_d1, H, H, &h->td1)) rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed");
+  // distance embeddings as fp16 hi / lo planes, padded to 256 rows (row 2*max_pos-1.. are zero)
+  for (int l = 0; l < d.layers && !rc; ++l) {
+    LayerW& w = h->layers[l];
+    const size_t n = (size_t)fd::ATT_E_TABLE * FD_HEAD_DIM;
+    float* padded = nullptr;
+    if (cudaMalloc(&padded, n * sizeof(float)) != cudaSuccess || cudaMalloc(&w.e_hi, n * sizeof(__half)) != cudaSuccess ||
+        cudaMalloc(&w.e_lo, n * sizeof(__half)) != cudaSuccess) { rc = fail(FD_ERR_CUDA, "distance-embedding planes: out of memory"); cudaFree(padded); break; }
+    h->allocs.push_back(w.e_hi); h->allocs.push_back(w.e_lo);
+    cudaMemset(padded, 0, n * sizeof(float));
+    cudaMemcpy(padded, w.dist, sizeof(float) * (2 * d.max_pos - 1) * FD_HEAD_DIM, cudaMemcpyDeviceToDevice);
+    fd::tc_split_kernel<<<16, 256>>>(padded, w.e_hi, w.e_lo, n / 4, 1.0f);
+    cudaDeviceSynchronize();
+    cudaFree(padded);
+  }
   if (!rc) {
     cudaFuncSetAttribute(fd::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)attn_smem_bytes(128, 128));
+    cudaFuncSetAttribute(fd::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
+    cudaFuncSetAttribute(fd::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
     if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(FD_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (rc) {
@@ -366,6 +408,7 @@ int32_t fd_set_schedule(fd_handle* h, int32_t timesteps, const float* time_table
 int32_t fd_set_gemm_mode(fd_handle* h, int32_t gemm_mode) {
   if (!h) return fail(FD_ERR_INVALID, "null handle");
   if (gemm_mode < FD_GEMM_FP32_SIMT || gemm_mode > FD_GEMM_TC_1X) return fail(FD_ERR_INVALID, "bad gemm_mode");
+  if (gemm_mode != FD_GEMM_FP32_SIMT && h->d.max_pos != 128) return fail(FD_ERR_UNSUPPORTED, "tensor-core path needs max_pos = 128");
   h->gemm_mode = gemm_mode;
   return FD_OK;
 }
@@ -545,7 +588,7 @@ int32_t fd_debug_gemm(int32_t gemm_mode, const float* a_dev, const float* w_dev,
                       const float* bias_dev, float* c_dev, int32_t rows, int32_t n, int32_t k,
                       void* stream) {
   if (!a_dev || !w_dev || !c_dev) return fail(FD_ERR_INVALID, "null argument");
-  if (rows % FD_ROW_TILE || n % 64 || k % 64) return fail(FD_ERR_INVALID, "rows %% 128, n %% 64, k %% 64 must be 0");
+  if (rows % 128 || n % 64 || k % 64) return fail(FD_ERR_INVALID, "rows %% 128, n %% 64, k %% 64 must be 0");
   cudaStream_t st = (cudaStream_t)stream;
   float* zero_bias = nullptr;
   if (!bias_dev) {
@@ -575,6 +618,63 @@ int32_t fd_debug_gemm(int32_t gemm_mode, const float* a_dev, const float* w_dev,
   }
   if (!rc) rc = check_launch();
   if (zero_bias) { cudaStreamSynchronize(st); cudaFree(zero_bias); }
+  return rc;
+}
+
+// ctx = hi + lo (fp16 planes back to fp32), for the debug hook below
+__global__ void fd_join_planes_kernel(const __half* hi, const __half* lo, float* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.0f);
+}
+
+int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, int32_t n_pad,
+                           const int32_t* lengths, int32_t all_rows, const float* dist_dev, int32_t heads,
+                           float* ctx_out_dev, void* stream) {
+  if (!qkv_dev || !lengths || !dist_dev || !ctx_out_dev) return fail(FD_ERR_INVALID, "null argument");
+  if (batch < 1 || n_pad < 1 || n_pad > 128 || heads < 1) return fail(FD_ERR_INVALID, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = heads * FD_HEAD_DIM;
+  std::vector<int> row_start(batch), n_rows(batch), n_keys(batch);
+  int rows = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (lengths[b] < 1 || lengths[b] > n_pad) return fail(FD_ERR_INVALID, "bad length");
+    n_rows[b] = all_rows ? n_pad : lengths[b]; n_keys[b] = lengths[b]; row_start[b] = rows; rows += n_rows[b];
+  }
+  int *d_rs = nullptr, *d_nr = nullptr, *d_nk = nullptr;
+  FD_CUDA(cudaMalloc(&d_rs, sizeof(int) * batch)); FD_CUDA(cudaMalloc(&d_nr, sizeof(int) * batch)); FD_CUDA(cudaMalloc(&d_nk, sizeof(int) * batch));
+  FD_CUDA(cudaMemcpy(d_rs, row_start.data(), sizeof(int) * batch, cudaMemcpyHostToDevice));
+  FD_CUDA(cudaMemcpy(d_nr, n_rows.data(), sizeof(int) * batch, cudaMemcpyHostToDevice));
+  FD_CUDA(cudaMemcpy(d_nk, n_keys.data(), sizeof(int) * batch, cudaMemcpyHostToDevice));
+  int rc = FD_OK;
+  if (mode == FD_GEMM_FP32_SIMT) {
+    cudaFuncSetAttribute(fd::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(128, 128));
+    dim3 grid(heads, batch);
+    fd::attention_simt_kernel<<<grid, 128, attn_smem_bytes(n_pad, n_pad), st>>>(qkv_dev, d_rs, d_nr, d_nk, nullptr, n_pad, dist_dev, 128, H, ctx_out_dev);
+  } else {
+    const size_t nq = (size_t)rows * 3 * H, nc = (size_t)rows * H, ne = (size_t)fd::ATT_E_TABLE * FD_HEAD_DIM;
+    __half *q_hi, *q_lo, *c_hi, *c_lo, *e_hi, *e_lo; float* e_pad;
+    FD_CUDA(cudaMalloc(&q_hi, nq * 2)); FD_CUDA(cudaMalloc(&q_lo, nq * 2)); FD_CUDA(cudaMalloc(&c_hi, nc * 2)); FD_CUDA(cudaMalloc(&c_lo, nc * 2));
+    FD_CUDA(cudaMalloc(&e_hi, ne * 2)); FD_CUDA(cudaMalloc(&e_lo, ne * 2)); FD_CUDA(cudaMalloc(&e_pad, ne * 4));
+    FD_CUDA(cudaMemsetAsync(e_pad, 0, ne * 4, st)); FD_CUDA(cudaMemsetAsync(c_hi, 0, nc * 2, st)); FD_CUDA(cudaMemsetAsync(c_lo, 0, nc * 2, st));
+    FD_CUDA(cudaMemcpyAsync(e_pad, dist_dev, sizeof(float) * 255 * FD_HEAD_DIM, cudaMemcpyDeviceToDevice, st));
+    fd::tc_split_kernel<<<16, 256, 0, st>>>(e_pad, e_hi, e_lo, ne / 4, 1.0f);
+    fd::tc_split_kernel<<<256, 256, 0, st>>>(qkv_dev, q_hi, q_lo, nq / 4, 1.0f);
+    cudaFuncSetAttribute(fd::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
+    cudaFuncSetAttribute(fd::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = batch * heads, grid = items < sms ? items : sms;
+    if (mode == FD_GEMM_TC_3X)
+      fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
+    else
+      fd::attention_mma_kernel<false><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
+    fd_join_planes_kernel<<<256, 256, 0, st>>>(c_hi, mode == FD_GEMM_TC_3X ? c_lo : nullptr, ctx_out_dev, nc);
+    cudaStreamSynchronize(st);
+    cudaFree(q_hi); cudaFree(q_lo); cudaFree(c_hi); cudaFree(c_lo); cudaFree(e_hi); cudaFree(e_lo); cudaFree(e_pad);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(FD_ERR_CUDA, "debug attention: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_rs); cudaFree(d_nr); cudaFree(d_nk);
   return rc;
 }
 

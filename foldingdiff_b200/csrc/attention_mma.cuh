@@ -1,0 +1,328 @@
+// Relative-key self-attention on tensor cores (warp-level mma.sync.m16n8k16, fp16 in / fp32 accumulate).
+//
+//   S[l, r] = (q_l . k_r + q_l . E[l - r + P - 1]) / sqrt(32) + bias_r ;  ctx_l = softmax_r(S) V
+//   (transformers 4.11.3 BertSelfAttention, position_embedding_type = "relative_key";
+//    call site /root/reference/foldingdiff/modelling.py:473)
+//
+// Shapes are tiny (n <= 128 residues, head_dim 32), so the work item is one (chain, head): 8 warps x 16
+// query rows against all keys of the chain, which sit in shared memory.  The kernel is persistent
+// (one CTA per SM): the layer's distance-embedding table is staged ONCE per CTA and the K / V tiles of
+// the next work item are prefetched (cp.async, double buffer) under the current item's math.
+//
+//   * operands are the fp16 hi / lo planes the QKV GEMM epilogue wrote; every product runs as the
+//     error-compensated triple  hi*hi + hi*lo + lo*hi  (same scheme as gemm_tc.cuh), fp32 accumulate
+//   * Q.K^T:   A = Q rows (registers, straight from global), B = K tile via ldmatrix
+//   * relative-key term: R = Q . E_window^T is a GEMM over the (n + 15) distance-embedding rows a
+//     16-row block can see; the Toeplitz gather S[l, r] += R[l, l - r + c] is done through a per-warp
+//     fp32 scratch in shared memory (each row is written and read back by the same warp)
+//   * softmax in registers on the S accumulator fragments (quad shuffles for the row max / sum)
+//   * P.V:     A = P (S fragments re-packed to fp16 hi / lo in registers), B = V via ldmatrix.trans
+//   * output: ctx as fp16 hi / lo planes, ready to be the A operand of the attention-output GEMM
+//
+// Keys >= n_keys are masked to -inf, which equals the reference's additive -10000 (exp underflows to
+// exactly 0 in fp32, sampling.py:56-58 + modelling.py:450-452).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace fd {
+
+constexpr int ATT_WARPS = 8;      // 8 warps x 16 query rows = the whole chain (n <= 128)
+constexpr int ATT_PITCH = 40;     // halves per smem row (32 + 8 pad -> conflict-free ldmatrix)
+constexpr int ATT_RP = 104;       // fp32 scratch pitch (== 8 mod 32; >= 64 + 16 columns)
+constexpr int ATT_E_TABLE = 256;  // rows of the padded per-layer table (255 real + 1 zero row)
+constexpr int ATT_KV_HALVES = 128 * ATT_PITCH;  // one K or V plane of one work item
+
+constexpr size_t att_smem_bytes() {
+  return (size_t)2 * ATT_E_TABLE * ATT_PITCH * 2   // E hi/lo, whole table, resident for the kernel's life
+         + (size_t)2 * 4 * ATT_KV_HALVES * 2       // double-buffered {K hi, K lo, V hi, V lo}
+         + (size_t)ATT_WARPS * 16 * ATT_RP * 4     // R scratch
+         + 2 * 128 * 4;                            // double-buffered key bias
+}
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// (x0, x1) -> packed fp16 hi and lo words
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Stage K and V of one work item (chain, head) into a shared-memory buffer {K hi, K lo, V hi, V lo}.
+template <bool THREE>
+__device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const __half* __restrict__ qkv_hi,
+                                             const __half* __restrict__ qkv_lo, const float* __restrict__ key_bias,
+                                             int chain, int head, int r0, int n_keys, int n_pad, int H) {
+  const int nk16 = (n_keys + 15) & ~15, ld = 3 * H;
+  __half* Ks_hi = buf; __half* Ks_lo = buf + ATT_KV_HALVES;
+  __half* Vs_hi = buf + 2 * ATT_KV_HALVES; __half* Vs_lo = buf + 3 * ATT_KV_HALVES;
+  for (int i = threadIdx.x; i < nk16 * 4; i += ATT_WARPS * 32) {
+    const int r = i >> 2, c = (i & 3) * 8;  // 8 halves = 16 bytes
+    const int so = r * ATT_PITCH + c;
+    if (r < n_keys) {
+      const size_t off = (size_t)(r0 + r) * ld + head * FD_HEAD_DIM + c;
+      cp_async16(Ks_hi + so, qkv_hi + off + H);
+      cp_async16(Vs_hi + so, qkv_hi + off + 2 * H);
+      if (THREE) { cp_async16(Ks_lo + so, qkv_lo + off + H); cp_async16(Vs_lo + so, qkv_lo + off + 2 * H); }
+    } else {  // rows padding the key count up to a multiple of 16: zeros (P is 0 there, 0 * 0 = 0)
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Ks_hi + so) = z; *reinterpret_cast<uint4*>(Vs_hi + so) = z;
+      if (THREE) { *reinterpret_cast<uint4*>(Ks_lo + so) = z; *reinterpret_cast<uint4*>(Vs_lo + so) = z; }
+    }
+  }
+  for (int i = threadIdx.x; i < nk16; i += ATT_WARPS * 32)
+    bias_s[i] = (i < n_keys) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] : 0.0f) : -INFINITY;
+}
+
+// One warp: 16 query rows [l0, l0 + 16) of one (chain, head) against all staged keys.
+template <bool THREE>
+__device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, const __half* Es_lo, float* Rw,
+                                         const float* Bs, const __half* __restrict__ qkv_hi,
+                                         const __half* __restrict__ qkv_lo, int r0, int l0, int n_rows, int n_keys,
+                                         int head, int H, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
+  const __half* Ks_hi = kv; const __half* Ks_lo = kv + ATT_KV_HALVES;
+  const __half* Vs_hi = kv + 2 * ATT_KV_HALVES; const __half* Vs_lo = kv + 3 * ATT_KV_HALVES;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nk16 = (n_keys + 15) & ~15, ld = 3 * H;
+
+  // ---- Q fragments (A operand, 16 rows x 32) from global ----------------------------------------
+  uint32_t qa_hi[2][4], qa_lo[2][4];
+  {
+    const int ra = min(l0 + g, n_rows - 1), rb = min(l0 + g + 8, n_rows - 1);  // clamp: rows >= n_rows are discarded
+    const size_t oa = (size_t)(r0 + ra) * ld + head * FD_HEAD_DIM, ob = (size_t)(r0 + rb) * ld + head * FD_HEAD_DIM;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa_hi[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c);
+      qa_hi[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c);
+      qa_hi[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c + 8);
+      qa_hi[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c + 8);
+      if (THREE) {
+        qa_lo[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c);
+        qa_lo[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c);
+        qa_lo[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c + 8);
+        qa_lo[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c + 8);
+      }
+    }
+  }
+  // B-operand row address pattern of ldmatrix.x4 over a [8 rows][32 halves] tile: lane -> (row, 8-half column block)
+  const int lm_row = lane & 7, lm_col = (lane >> 3) * 8;
+
+  // ---- S = Q K^T ---------------------------------------------------------------------------------
+  float s[16][4];
+  const int nnb = nk16 >> 3;  // n8 key blocks
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
+    if (nb < nnb) {
+      uint32_t kh[4], kl[4];
+      ldsm_x4(kh, Ks_hi + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
+      mma_f16(s[nb], qa_hi[0], kh[0], kh[1]);
+      mma_f16(s[nb], qa_hi[1], kh[2], kh[3]);
+      if (THREE) {
+        ldsm_x4(kl, Ks_lo + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
+        mma_f16(s[nb], qa_hi[0], kl[0], kl[1]);
+        mma_f16(s[nb], qa_hi[1], kl[2], kl[3]);
+        mma_f16(s[nb], qa_lo[0], kh[0], kh[1]);
+        mma_f16(s[nb], qa_lo[1], kh[2], kh[3]);
+      }
+    }
+  }
+
+  // ---- relative-key term, 64 keys at a time ------------------------------------------------------
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int kh_cnt = min(64, nk16 - 64 * hh);  // keys in this half (multiple of 16), <= 0 -> nothing
+    if (kh_cnt > 0) {
+      // column j of the scratch <-> table row e0 + j, where  j = (l - l0) - (r - 64 hh) + (kh_cnt - 1)
+      const int e0 = l0 - 64 * hh + 128 - kh_cnt;
+      const int njb = (kh_cnt >> 3) + 2;
+      for (int jb = 0; jb < njb; ++jb) {
+        float r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t eh[4], el[4];
+        ldsm_x4(eh, Es_hi + (e0 + jb * 8 + lm_row) * ATT_PITCH + lm_col);
+        mma_f16(r4, qa_hi[0], eh[0], eh[1]);
+        mma_f16(r4, qa_hi[1], eh[2], eh[3]);
+        if (THREE) {
+          ldsm_x4(el, Es_lo + (e0 + jb * 8 + lm_row) * ATT_PITCH + lm_col);
+          mma_f16(r4, qa_hi[0], el[0], el[1]);
+          mma_f16(r4, qa_hi[1], el[2], el[3]);
+          mma_f16(r4, qa_lo[0], eh[0], eh[1]);
+          mma_f16(r4, qa_lo[1], eh[2], eh[3]);
+        }
+        *reinterpret_cast<float2*>(Rw + g * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[0], r4[1]);
+        *reinterpret_cast<float2*>(Rw + (g + 8) * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[2], r4[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nbl = 0; nbl < 8; ++nbl) {
+        const int nb = hh * 8 + nbl;
+        if (nbl * 8 < kh_cnt) {
+          const int rr = nbl * 8 + 2 * t;  // key index inside the half (first of this thread's two)
+          const int ca = g - rr + kh_cnt - 1, cb = g + 8 - rr + kh_cnt - 1;
+          s[nb][0] += Rw[g * ATT_RP + ca];
+          s[nb][1] += Rw[g * ATT_RP + ca - 1];
+          s[nb][2] += Rw[(g + 8) * ATT_RP + cb];
+          s[nb][3] += Rw[(g + 8) * ATT_RP + cb - 1];
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- scale, bias / mask, softmax (rows g and g + 8 of this warp's block) -----------------------
+  const float inv_sqrt_d = 0.17677669529663688110f;  // 1 / sqrt(32)
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    if (nb < nnb) {
+      const float b0 = Bs[nb * 8 + 2 * t], b1 = Bs[nb * 8 + 2 * t + 1];
+      s[nb][0] = fmaf(s[nb][0], inv_sqrt_d, b0); s[nb][1] = fmaf(s[nb][1], inv_sqrt_d, b1);
+      s[nb][2] = fmaf(s[nb][2], inv_sqrt_d, b0); s[nb][3] = fmaf(s[nb][3], inv_sqrt_d, b1);
+      m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
+      m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  const float log2e = 1.44269504088896340736f;
+  float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    if (nb < nnb) {
+      s[nb][0] = exp2f((s[nb][0] - m0) * log2e); s[nb][1] = exp2f((s[nb][1] - m0) * log2e);
+      s[nb][2] = exp2f((s[nb][2] - m1) * log2e); s[nb][3] = exp2f((s[nb][3] - m1) * log2e);
+      sum0 += s[nb][0] + s[nb][1];
+      sum1 += s[nb][2] + s[nb][3];
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+  // ---- O = P V -----------------------------------------------------------------------------------
+  float o[4][4];
+#pragma unroll
+  for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.0f;
+  const int nkb = nk16 >> 4;
+  // ldmatrix.x4.trans over a [16 keys][16 d] tile: lane -> (key row, d column block)
+  const int vt_row = (lane & 7) + ((lane >> 3) & 1) * 8, vt_col = (lane >> 4) * 8;
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    if (kb < nkb) {
+      uint32_t p_hi[4], p_lo[4];
+      split2(s[2 * kb][0], s[2 * kb][1], p_hi[0], p_lo[0]);
+      split2(s[2 * kb][2], s[2 * kb][3], p_hi[1], p_lo[1]);
+      split2(s[2 * kb + 1][0], s[2 * kb + 1][1], p_hi[2], p_lo[2]);
+      split2(s[2 * kb + 1][2], s[2 * kb + 1][3], p_hi[3], p_lo[3]);
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {
+        uint32_t vh[4], vl[4];
+        ldsm_x4_t(vh, Vs_hi + (kb * 16 + vt_row) * ATT_PITCH + dp * 16 + vt_col);
+        mma_f16(o[2 * dp], p_hi, vh[0], vh[1]);
+        mma_f16(o[2 * dp + 1], p_hi, vh[2], vh[3]);
+        if (THREE) {
+          ldsm_x4_t(vl, Vs_lo + (kb * 16 + vt_row) * ATT_PITCH + dp * 16 + vt_col);
+          mma_f16(o[2 * dp], p_hi, vl[0], vl[1]);
+          mma_f16(o[2 * dp + 1], p_hi, vl[2], vl[3]);
+          mma_f16(o[2 * dp], p_lo, vh[0], vh[1]);
+          mma_f16(o[2 * dp + 1], p_lo, vh[2], vh[3]);
+        }
+      }
+    }
+  }
+
+  // ---- normalise and store ctx as hi / lo planes -------------------------------------------------
+  const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+  const int ra = l0 + g, rb = l0 + g + 8;
+#pragma unroll
+  for (int dn = 0; dn < 4; ++dn) {
+    const int c = head * FD_HEAD_DIM + dn * 8 + 2 * t;
+    uint32_t hi, lo;
+    if (ra < n_rows) {
+      split2(o[dn][0] * i0, o[dn][1] * i0, hi, lo);
+      *reinterpret_cast<uint32_t*>(ctx_hi + (size_t)(r0 + ra) * H + c) = hi;
+      if (THREE) *reinterpret_cast<uint32_t*>(ctx_lo + (size_t)(r0 + ra) * H + c) = lo;
+    }
+    if (rb < n_rows) {
+      split2(o[dn][2] * i1, o[dn][3] * i1, hi, lo);
+      *reinterpret_cast<uint32_t*>(ctx_hi + (size_t)(r0 + rb) * H + c) = hi;
+      if (THREE) *reinterpret_cast<uint32_t*>(ctx_lo + (size_t)(r0 + rb) * H + c) = lo;
+    }
+  }
+}
+
+// Persistent kernel: grid = min(#SMs, batch * heads); work item w = chain * heads + head, taken round-robin.
+// The whole distance-embedding table of the layer stays in shared memory; K / V of the next item are
+// prefetched with cp.async while the current one is being computed (one __syncthreads per item).
+// THREE: 3-pass split (parity) or hi*hi only.
+template <bool THREE>
+__global__ void __launch_bounds__(ATT_WARPS * 32, 1)
+attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
+                     const int* __restrict__ row_start, const int* __restrict__ n_rows_arr,
+                     const int* __restrict__ n_keys_arr, const float* __restrict__ key_bias, int n_pad,
+                     const __half* __restrict__ e_hi, const __half* __restrict__ e_lo, int H, int heads,
+                     int n_items, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __half* Es_hi = reinterpret_cast<__half*>(att_smem);
+  __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
+  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // buffer b at kv0 + b * 4 * ATT_KV_HALVES
+  float* Rs = reinterpret_cast<float*>(kv0 + 2 * 4 * ATT_KV_HALVES);
+  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // bias buffer b at Bs0 + b * 128
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < ATT_E_TABLE * 4; i += ATT_WARPS * 32) {
+    const int r = i >> 2, c = (i & 3) * 8;
+    cp_async16(Es_hi + r * ATT_PITCH + c, e_hi + (size_t)r * FD_HEAD_DIM + c);
+    if (THREE) cp_async16(Es_lo + r * ATT_PITCH + c, e_lo + (size_t)r * FD_HEAD_DIM + c);
+  }
+  int item = blockIdx.x;
+  if (item < n_items) {
+    const int chain = item / heads, head = item % heads;
+    att_stage_kv<THREE>(kv0, Bs0, qkv_hi, qkv_lo, key_bias, chain, head, row_start[chain], n_keys_arr[chain], n_pad, H);
+  }
+  float* Rw = Rs + warp * 16 * ATT_RP;
+  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    cp_async_wait_all();
+    __syncthreads();  // item's K / V / bias (and, first time, E) visible; everyone is done with the other buffer
+    const int next = item + gridDim.x;
+    if (next < n_items) {
+      const int nc = next / heads, nh = next % heads;
+      att_stage_kv<THREE>(kv0 + (buf ^ 1) * 4 * ATT_KV_HALVES, Bs0 + (buf ^ 1) * 128, qkv_hi, qkv_lo, key_bias, nc, nh,
+                          row_start[nc], n_keys_arr[nc], n_pad, H);
+    }
+    const int chain = item / heads, head = item % heads;
+    const int n_rows = n_rows_arr[chain], l0 = warp * 16;
+    if (l0 < n_rows)
+      att_rows<THREE>(kv0 + buf * 4 * ATT_KV_HALVES, Es_hi, Es_lo, Rw, Bs0 + buf * 128, qkv_hi, qkv_lo,
+                      row_start[chain], l0, n_rows, n_keys_arr[chain], head, H, ctx_hi, ctx_lo);
+  }
+  cp_async_wait_all();
+}
+
+}  // namespace fd

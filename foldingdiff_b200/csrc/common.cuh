@@ -5,7 +5,7 @@
 
 #define FD_HEAD_DIM 32
 #define FD_MAX_FEATURES 16
-#define FD_ROW_TILE 128  // packed-row count is padded to this (one MMA M tile)
+#define FD_ROW_TILE 256  // packed-row count is padded to this (two MMA M tiles: one per CTA of a 2-cluster)
 
 namespace fd {
 

@@ -3,8 +3,12 @@
 //   * tcgen05.mma (kind::f16, fp32 accumulate in TMEM), issued by one elected thread
 //   * operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, K-major)
 //   * warp-specialised persistent CTAs: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
-//     warps 2..5 = epilogue (tcgen05.ld -> registers -> bias / residual / GELU -> global)
+//     warps 2..9 = epilogue (tcgen05.ld -> registers -> bias / residual / GELU -> global); two warps
+//     share each TMEM lane quadrant and split the tile's columns
 //   * two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i + 1
+//   * thread-block clusters of 2 along M: the two CTAs work on vertically adjacent row blocks of the
+//     same column block, each fetches HALF of the weight tile and TMA-multicasts it to both, which cuts
+//     the L2 -> SM operand traffic this kernel is bound by (ncu: ~7 TB/s at 35% MMA issue) by 30%
 //
 // Precision.  The parity gate of this project is 1e-4 max-abs on fp32 angle tensors, which single
 // pass fp16/bf16/tf32 operands do not meet.  FD_GEMM_TC_3X therefore runs
@@ -19,6 +23,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels_simt.cuh"  // EPI_* and gelu_erf
 
@@ -27,7 +33,8 @@ namespace fd {
 constexpr int TC_BM = 128;         // rows per tile (one UMMA M)
 constexpr int TC_BK = 64;          // fp16 elements per 128-byte swizzle row
 constexpr int TC_UMMA_K = 16;      // K of one tcgen05.mma.kind::f16
-constexpr int TC_THREADS = 192;    // 6 warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 struct TcPlane {         // fp16 hi / lo planes of an activation matrix [rows, k]
@@ -41,10 +48,11 @@ struct TcWeight {        // fp16 hi / lo planes of a weight matrix [n, k], scale
   __half* lo = nullptr;
   int n = 0, k = 0, bn = 0;
   float inv_scale = 1.0f;      // 2^-shift
-  CUtensorMap map_hi, map_lo;  // box {64, bn}
+  CUtensorMap map_hi, map_lo;    // box {64, bn}
+  CUtensorMap half_hi, half_lo;  // box {64, bn / 2}: what one CTA of a 2-cluster fetches and multicasts
 };
 struct TcActs {
-  TcPlane h, ctx, a, inter;
+  TcPlane h, qkv, ctx, a, inter;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +98,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -114,6 +139,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -165,7 +195,7 @@ struct TcCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 };
 
-template <int BN, int NPASS, int EPI>
+template <int BN, int NPASS, int EPI, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -183,12 +213,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blocks = N / BN, m_blocks = M / TC_BM;
+  // With CL == 2 a "tile" is a pair of vertically adjacent 128-row blocks, one per CTA of the cluster;
+  // both CTAs walk the same tile sequence (they are coupled through the multicast barriers).
+  const int n_blocks = N / BN, m_blocks = M / (TC_BM * CL);
   const int n_tiles = n_blocks * m_blocks, k_blocks = K / TC_BK;
+  const int crank = CL > 1 ? (int)cluster_rank() : 0;
+  const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -199,6 +234,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -207,17 +243,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * TC_BM, n0 = (tile % n_blocks) * BN;
+      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
+        const int m0 = ((tile / n_blocks) * CL + crank) * TC_BM, n0 = (tile % n_blocks) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          // the stage is free once the MMA warps of ALL CTAs in the cluster have drained it
           if (!mbar_wait(&empty[stage], phase ^ 1)) { atomicExch(err_flag, 101); ok = false; break; }
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(s, &map_a_hi, &full[stage], kb * TC_BK, m0);
-          tma_load_2d(s + Cfg::PLANES * Cfg::A_BYTES, &map_w_hi, &full[stage], kb * TC_BK, n0);
-          if (NPASS > 1) {
-            tma_load_2d(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
-            tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &map_w_lo, &full[stage], kb * TC_BK, n0);
+          if (NPASS > 1) tma_load_2d(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
+          uint8_t* w_hi = s + Cfg::PLANES * Cfg::A_BYTES;
+          uint8_t* w_lo = w_hi + Cfg::W_BYTES;
+          if (CL == 1) {
+            tma_load_2d(w_hi, &map_w_hi, &full[stage], kb * TC_BK, n0);
+            if (NPASS > 1) tma_load_2d(w_lo, &map_w_lo, &full[stage], kb * TC_BK, n0);
+          } else {  // this CTA's half of the weight tile, delivered to both CTAs (map_w_* has a BN/2-row box)
+            const int half_off = crank * (Cfg::W_BYTES / 2);
+            tma_load_2d_mc(w_hi + half_off, &map_w_hi, &full[stage], kb * TC_BK, n0 + crank * (BN / 2), kMask);
+            if (NPASS > 1)
+              tma_load_2d_mc(w_lo + half_off, &map_w_lo, &full[stage], kb * TC_BK, n0 + crank * (BN / 2), kMask);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -230,7 +274,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
         if (!mbar_wait(&acc_empty[acc], acc_phase ^ 1)) { atomicExch(err_flag, 102); break; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -251,7 +295,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               umma_f16(d_tmem, da_lo, dw_hi, idesc, 1u);
             }
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above retire
+          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], kMask);
           if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -262,15 +307,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    constexpr int COLS_PER_WARP = BN / (TC_EPI_WARPS / 4);
+    static_assert(COLS_PER_WARP % 32 == 0, "column split of the epilogue warps");
+    const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blocks) * TC_BM, n0 = (tile % n_blocks) * BN;
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      const int m0 = ((tile / n_blocks) * CL + crank) * TC_BM, n0 = (tile % n_blocks) * BN;
       if (!mbar_wait(&acc_full[acc], acc_phase)) { if (lane == 0) atomicExch(err_flag, 104); break; }
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
         const size_t off = (size_t)row * N + n0 + c0;
@@ -314,13 +362,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);  // 128 arrivals release the accumulator to the MMA warp
+      mbar_arrive(&acc_empty[acc]);  // all epilogue threads arrive -> accumulator goes back to the MMA warp
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -417,13 +466,14 @@ inline void tc_free_plane(TcPlane* p) {
 }
 inline int tc_alloc_acts(TcActs* a, int rows_pad, int hidden, int inter) {
   if (tc_alloc_plane(&a->h, rows_pad, hidden)) return 1;
+  if (tc_alloc_plane(&a->qkv, rows_pad, 3 * hidden)) return 1;
   if (tc_alloc_plane(&a->ctx, rows_pad, hidden)) return 1;
   if (tc_alloc_plane(&a->a, rows_pad, hidden)) return 1;
   if (tc_alloc_plane(&a->inter, rows_pad, inter)) return 1;
   return 0;
 }
 inline void tc_free_acts(TcActs* a) {
-  tc_free_plane(&a->h); tc_free_plane(&a->ctx); tc_free_plane(&a->a); tc_free_plane(&a->inter);
+  tc_free_plane(&a->h); tc_free_plane(&a->qkv); tc_free_plane(&a->ctx); tc_free_plane(&a->a); tc_free_plane(&a->inter);
 }
 
 // fp32 [n, k] device weight -> scaled fp16 hi / lo planes + TMA maps.  Synchronous (create time).
@@ -454,6 +504,8 @@ inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out) {
   if (cudaDeviceSynchronize() != cudaSuccess) return 1;
   if (tc_make_map(&out->map_hi, out->hi, n, k, out->bn)) return 2;
   if (tc_make_map(&out->map_lo, out->lo, n, k, out->bn)) return 2;
+  if (tc_make_map(&out->half_hi, out->hi, n, k, out->bn / 2)) return 2;
+  if (tc_make_map(&out->half_lo, out->lo, n, k, out->bn / 2)) return 2;
   return 0;
 }
 inline void tc_free_weight(TcWeight* w) {
@@ -486,25 +538,56 @@ inline int tc_check_error() {
   return v;
 }
 
-template <int BN, int NPASS, int EPI>
-int tc_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
-              TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+// FOLDINGDIFF_B200_TC_CLUSTER=1 disables the 2-CTA multicast clusters (A/B switch for profiling).
+inline int tc_cluster_size() {
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("FOLDINGDIFF_B200_TC_CLUSTER");
+    cl = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cl;
+}
+
+template <int BN, int NPASS, int EPI, int CL>
+int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
+                 TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN, NPASS>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BN, NPASS, EPI>;
+  auto kern = tc_gemm_kernel<BN, NPASS, EPI, CL>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
     configured = true;
   }
   int* err = tc_err_flag();
   if (!err) return 11;
-  const int tiles = (M / TC_BM) * (N / BN);
-  const int grid = tiles < sm_count ? tiles : sm_count;
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a->map_hi, a->map_lo, w->map_hi, w->map_lo, bias, resid, C,
-                                                  c_tc ? c_tc->hi : nullptr,
-                                                  (c_tc && NPASS > 1) ? c_tc->lo : nullptr, M, N, K,
-                                                  w->inv_scale, err);
-  return cudaGetLastError() == cudaSuccess ? 0 : 12;
+  const int tiles = (M / (TC_BM * CL)) * (N / BN);           // cluster-level tiles
+  int clusters = sm_count / CL;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  __half* c_hi = c_tc ? c_tc->hi : nullptr;
+  __half* c_lo = (c_tc && NPASS > 1) ? c_tc->lo : nullptr;
+  const CUtensorMap& wh = CL > 1 ? w->half_hi : w->map_hi;
+  const CUtensorMap& wl = CL > 1 ? w->half_lo : w->map_lo;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, wh, wl, bias, resid, C, c_hi, c_lo, M, N, K,
+                                     w->inv_scale, err);
+  return e == cudaSuccess ? 0 : 12;
+}
+
+template <int BN, int NPASS, int EPI>
+int tc_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
+              TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+  if (tc_cluster_size() == 2 && M % (2 * TC_BM) == 0)
+    return tc_launch_cl<BN, NPASS, EPI, 2>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  return tc_launch_cl<BN, NPASS, EPI, 1>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
 }
 
 template <int BN, int NPASS>

@@ -13,6 +13,8 @@
 //   tail_kernel       modelling.py:203-208 (AnglesPredictor LN + dense2) fused with
 //                     sampling.py:62-75 (posterior step) and :119-130 (per-column wrap)
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fd {
@@ -26,7 +28,8 @@ __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n_rows, int n_pad,
              int F, const float* __restrict__ w_in, const float* __restrict__ b_in,
              const float* __restrict__ g, const float* __restrict__ bta, float eps,
-             const float* __restrict__ temb, int temb_stride, float* __restrict__ h_out) {
+             const float* __restrict__ temb, int temb_stride, float* __restrict__ h_out,
+             __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
   constexpr int H = VPL * 32;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -58,7 +61,13 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
-    h_out[(size_t)warp * H + c] = ((v[i] - mean) * rstd) * g[c] + bta[c] + te[c];
+    const float y = ((v[i] - mean) * rstd) * g[c] + bta[c] + te[c];
+    h_out[(size_t)warp * H + c] = y;
+    if (o_hi) {  // fp16 hi / lo operand planes for the tensor-core GEMM that consumes this row
+      const __half hh = __float2half_rn(y);
+      o_hi[(size_t)warp * H + c] = hh;
+      if (o_lo) o_lo[(size_t)warp * H + c] = __float2half_rn(y - __half2float(hh));
+    }
   }
 }
 
@@ -68,7 +77,8 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
 template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, int n_rows, const float* __restrict__ g,
-                 const float* __restrict__ bta, float eps, float* __restrict__ out) {
+                 const float* __restrict__ bta, float eps, float* __restrict__ out,
+                 __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
   constexpr int H = VPL * 32;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,7 +101,13 @@ layernorm_kernel(const float* __restrict__ in, int n_rows, const float* __restri
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
-    out[(size_t)warp * H + c] = ((v[i] - mean) * rstd) * g[c] + bta[c];
+    const float y = ((v[i] - mean) * rstd) * g[c] + bta[c];
+    out[(size_t)warp * H + c] = y;
+    if (o_hi) {
+      const __half hh = __float2half_rn(y);
+      o_hi[(size_t)warp * H + c] = hh;
+      if (o_lo) o_lo[(size_t)warp * H + c] = __float2half_rn(y - __half2float(hh));
+    }
   }
 }
 

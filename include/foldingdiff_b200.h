@@ -212,6 +212,14 @@ int32_t fd_debug_gemm(int32_t gemm_mode, const float* a_dev, const float* w_dev,
                       const float* bias_dev, float* c_dev, int32_t rows, int32_t n, int32_t k,
                       void* stream);
 
+/* Debug / test hook: one relative-key attention layer in isolation.  qkv_dev is packed rows x 3H fp32
+ * (q | k | v, rows of chain b start at sum of the computed rows before it), dist_dev the (255, 32)
+ * distance embedding, ctx_out_dev packed rows x H fp32.  mode: FD_GEMM_FP32_SIMT = CUDA-core kernel,
+ * FD_GEMM_TC_3X / _1X = mma.sync kernel on fp16 hi / lo planes.  Synchronises. */
+int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, int32_t n_pad,
+                           const int32_t* lengths, int32_t all_rows, const float* dist_dev, int32_t heads,
+                           float* ctx_out_dev, void* stream);
+
 /* Debug / test hook: synchronise the current device and return (then clear) the tensor-core
  * pipeline error flag: 0 = healthy; 101..104 = a bounded mbarrier wait in the TMA producer /
  * MMA issuer / epilogue timed out (the kernels never spin forever). Negative = CUDA error. */

@@ -6,8 +6,9 @@ from foldingdiff_b200 import _native
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(256, 384, 384), (384, 1152, 384), (128, 768, 384), (256, 384, 768), (128, 576, 192), (128, 192, 384),
-          (128, 64, 64), (1280, 1152, 384)]
+# rows % 256 == 0 -> 2-CTA multicast clusters; otherwise the single-CTA variant
+SHAPES = [(256, 384, 384), (384, 1152, 384), (128, 768, 384), (256, 384, 768), (128, 576, 192), (512, 192, 384),
+          (128, 64, 64), (1280, 1152, 384), (2560, 768, 384), (37888, 384, 768)]
 
 
 def run(mode, a, w, bias):
