@@ -138,11 +138,11 @@ void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stri
 }
 
 template <int VPL>
-void launch_ln(fd_handle* H, const float* in, const float* g, const float* b, float* out,
+void launch_ln(fd_handle* H, const float* in, const float* resid, const float* g, const float* b, float* out,
                fd::TcPlane* planes, cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_LN, st);
-  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, H->rows, g, b, H->d.ln_eps, out,
+  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, resid, H->rows, g, b, H->d.ln_eps, out,
                                                     planes ? planes->hi : nullptr,
                                                     (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : nullptr);
   H->launches++;
@@ -181,7 +181,8 @@ void launch_attention(fd_handle* H, const float* dist, cudaStream_t st) {
 // tensor-core attention on the fp16 hi / lo planes (tc modes): qkv planes -> ctx planes
 void launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
   const int items = H->batch * H->d.heads;
-  const int grid = items < H->sm_count ? items : H->sm_count;
+  const int want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS;
+  const int grid = want < H->sm_count ? want : H->sm_count;
   const size_t smem = fd::att_smem_bytes();
   const float* bias = H->has_key_bias ? H->key_bias : nullptr;
   ProfScope ps(H, CAT_ATTN, st);
@@ -241,17 +242,17 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
     if (rc) return rc;
     if (tcm) launch_attention_mma(H, w, st);
     else launch_attention(H, w.dist, st);
-    rc = project(H, CAT_GEMM_OUT, fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp, Hd, Hd,
-                 &H->tc.ctx, nullptr, st);
+    rc = project(H, CAT_GEMM_OUT, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp,
+                 Hd, Hd, &H->tc.ctx, nullptr, st);
     if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
+    launch_ln<VPL>(H, H->tmp, tcm ? H->h : nullptr, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
     rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, tcm ? nullptr : H->inter,
                  I, Hd, &H->tc.a, tcm ? &H->tc.inter : nullptr, st);
     if (rc) return rc;
-    rc = project(H, CAT_GEMM_FFN2, fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a, H->tmp, Hd, I,
-                 &H->tc.inter, nullptr, st);
+    rc = project(H, CAT_GEMM_FFN2, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a, H->tmp,
+                 Hd, I, &H->tc.inter, nullptr, st);
     if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
+    launch_ln<VPL>(H, H->tmp, tcm ? H->a : nullptr, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
   }
   return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, &H->td1, H->b_d1, nullptr, H->tmp, Hd, Hd,
                  &H->tc.h, nullptr, st);
@@ -664,7 +665,7 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int items = batch * heads, grid = items < sms ? items : sms;
+    const int items = batch * heads, want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS, grid = want < sms ? want : sms;
     if (mode == FD_GEMM_TC_3X)
       fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
     else

@@ -6,8 +6,10 @@
 //
 // Shapes are tiny (n <= 128 residues, head_dim 32), so the work item is one (chain, head): 8 warps x 16
 // query rows against all keys of the chain, which sit in shared memory.  The kernel is persistent
-// (one CTA per SM): the layer's distance-embedding table is staged ONCE per CTA and the K / V tiles of
-// the next work item are prefetched (cp.async, double buffer) under the current item's math.
+// (one CTA per SM, 16 warps): the layer's distance-embedding table is staged ONCE per CTA, and the
+// CTA runs TWO independent 8-warp groups, each walking its own stream of work items - while one
+// group stages K / V of its next item, the other is in its math phase (ncu on the first version:
+// latency-bound at 8 warps / SM, dependent-MMA chains exposed).
 //
 //   * operands are the fp16 hi / lo planes the QKV GEMM epilogue wrote; every product runs as the
 //     error-compensated triple  hi*hi + hi*lo + lo*hi  (same scheme as gemm_tc.cuh), fp32 accumulate
@@ -28,17 +30,19 @@
 
 namespace fd {
 
-constexpr int ATT_WARPS = 8;      // 8 warps x 16 query rows = the whole chain (n <= 128)
+constexpr int ATT_GROUP_WARPS = 8;  // 8 warps x 16 query rows = the whole chain (n <= 128)
+constexpr int ATT_GROUPS = 2;       // independent warp groups per CTA
+constexpr int ATT_WARPS = ATT_GROUP_WARPS * ATT_GROUPS;
 constexpr int ATT_PITCH = 40;     // halves per smem row (32 + 8 pad -> conflict-free ldmatrix)
-constexpr int ATT_RP = 104;       // fp32 scratch pitch (== 8 mod 32; >= 64 + 16 columns)
+constexpr int ATT_RP = 72;        // fp32 scratch pitch (== 8 mod 32; >= 32 + 16 columns)
 constexpr int ATT_E_TABLE = 256;  // rows of the padded per-layer table (255 real + 1 zero row)
 constexpr int ATT_KV_HALVES = 128 * ATT_PITCH;  // one K or V plane of one work item
 
 constexpr size_t att_smem_bytes() {
-  return (size_t)2 * ATT_E_TABLE * ATT_PITCH * 2   // E hi/lo, whole table, resident for the kernel's life
-         + (size_t)2 * 4 * ATT_KV_HALVES * 2       // double-buffered {K hi, K lo, V hi, V lo}
-         + (size_t)ATT_WARPS * 16 * ATT_RP * 4     // R scratch
-         + 2 * 128 * 4;                            // double-buffered key bias
+  return (size_t)2 * ATT_E_TABLE * ATT_PITCH * 2      // E hi/lo, whole table, resident for the kernel's life
+         + (size_t)ATT_GROUPS * 4 * ATT_KV_HALVES * 2   // per group {K hi, K lo, V hi, V lo}
+         + (size_t)ATT_WARPS * 16 * ATT_RP * 4          // R scratch
+         + (size_t)ATT_GROUPS * 128 * 4;                // per group key bias
 }
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -78,10 +82,11 @@ template <bool THREE>
 __device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const __half* __restrict__ qkv_hi,
                                              const __half* __restrict__ qkv_lo, const float* __restrict__ key_bias,
                                              int chain, int head, int r0, int n_keys, int n_pad, int H) {
+  const int gtid = threadIdx.x & (ATT_GROUP_WARPS * 32 - 1);  // thread index inside the warp group
   const int nk16 = (n_keys + 15) & ~15, ld = 3 * H;
   __half* Ks_hi = buf; __half* Ks_lo = buf + ATT_KV_HALVES;
   __half* Vs_hi = buf + 2 * ATT_KV_HALVES; __half* Vs_lo = buf + 3 * ATT_KV_HALVES;
-  for (int i = threadIdx.x; i < nk16 * 4; i += ATT_WARPS * 32) {
+  for (int i = gtid; i < nk16 * 4; i += ATT_GROUP_WARPS * 32) {
     const int r = i >> 2, c = (i & 3) * 8;  // 8 halves = 16 bytes
     const int so = r * ATT_PITCH + c;
     if (r < n_keys) {
@@ -95,41 +100,46 @@ __device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const _
       if (THREE) { *reinterpret_cast<uint4*>(Ks_lo + so) = z; *reinterpret_cast<uint4*>(Vs_lo + so) = z; }
     }
   }
-  for (int i = threadIdx.x; i < nk16; i += ATT_WARPS * 32)
+  for (int i = gtid; i < nk16; i += ATT_GROUP_WARPS * 32)
     bias_s[i] = (i < n_keys) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] : 0.0f) : -INFINITY;
+}
+
+// Q fragments (A operand of m16n8k16: 16 rows x 32 head dims) of one warp, straight from global.
+// Issued BEFORE the K / V staging of the item so the L2 latency hides behind the cp.async wait.
+template <bool THREE>
+__device__ __forceinline__ void att_load_q(uint32_t (&qa_hi)[2][4], uint32_t (&qa_lo)[2][4],
+                                           const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
+                                           int r0, int l0, int n_rows, int head, int H) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, ld = 3 * H;
+  const int ra = min(l0 + g, n_rows - 1), rb = min(l0 + g + 8, n_rows - 1);  // clamp: rows >= n_rows are discarded
+  const size_t oa = (size_t)(r0 + ra) * ld + head * FD_HEAD_DIM, ob = (size_t)(r0 + rb) * ld + head * FD_HEAD_DIM;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    qa_hi[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c);
+    qa_hi[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c);
+    qa_hi[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c + 8);
+    qa_hi[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c + 8);
+    if (THREE) {
+      qa_lo[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c);
+      qa_lo[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c);
+      qa_lo[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c + 8);
+      qa_lo[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c + 8);
+    }
+  }
 }
 
 // One warp: 16 query rows [l0, l0 + 16) of one (chain, head) against all staged keys.
 template <bool THREE>
 __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, const __half* Es_lo, float* Rw,
-                                         const float* Bs, const __half* __restrict__ qkv_hi,
-                                         const __half* __restrict__ qkv_lo, int r0, int l0, int n_rows, int n_keys,
+                                         const float* Bs, const uint32_t (&qa_hi)[2][4], const uint32_t (&qa_lo)[2][4],
+                                         int r0, int l0, int n_rows, int n_keys,
                                          int head, int H, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
   const __half* Ks_hi = kv; const __half* Ks_lo = kv + ATT_KV_HALVES;
   const __half* Vs_hi = kv + 2 * ATT_KV_HALVES; const __half* Vs_lo = kv + 3 * ATT_KV_HALVES;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int nk16 = (n_keys + 15) & ~15, ld = 3 * H;
+  const int nk16 = (n_keys + 15) & ~15;
 
-  // ---- Q fragments (A operand, 16 rows x 32) from global ----------------------------------------
-  uint32_t qa_hi[2][4], qa_lo[2][4];
-  {
-    const int ra = min(l0 + g, n_rows - 1), rb = min(l0 + g + 8, n_rows - 1);  // clamp: rows >= n_rows are discarded
-    const size_t oa = (size_t)(r0 + ra) * ld + head * FD_HEAD_DIM, ob = (size_t)(r0 + rb) * ld + head * FD_HEAD_DIM;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int c = ks * 16 + 2 * t;
-      qa_hi[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c);
-      qa_hi[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c);
-      qa_hi[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_hi + oa + c + 8);
-      qa_hi[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_hi + ob + c + 8);
-      if (THREE) {
-        qa_lo[ks][0] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c);
-        qa_lo[ks][1] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c);
-        qa_lo[ks][2] = *reinterpret_cast<const uint32_t*>(qkv_lo + oa + c + 8);
-        qa_lo[ks][3] = *reinterpret_cast<const uint32_t*>(qkv_lo + ob + c + 8);
-      }
-    }
-  }
   // B-operand row address pattern of ldmatrix.x4 over a [8 rows][32 halves] tile: lane -> (row, 8-half column block)
   const int lm_row = lane & 7, lm_col = (lane >> 3) * 8;
 
@@ -144,24 +154,27 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
       ldsm_x4(kh, Ks_hi + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
       mma_f16(s[nb], qa_hi[0], kh[0], kh[1]);
       mma_f16(s[nb], qa_hi[1], kh[2], kh[3]);
-      if (THREE) {
+      if (THREE) {  // the two correction products get their own accumulators: three short independent chains
+        float x1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, x2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         ldsm_x4(kl, Ks_lo + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
-        mma_f16(s[nb], qa_hi[0], kl[0], kl[1]);
-        mma_f16(s[nb], qa_hi[1], kl[2], kl[3]);
-        mma_f16(s[nb], qa_lo[0], kh[0], kh[1]);
-        mma_f16(s[nb], qa_lo[1], kh[2], kh[3]);
+        mma_f16(x1, qa_hi[0], kl[0], kl[1]);
+        mma_f16(x2, qa_lo[0], kh[0], kh[1]);
+        mma_f16(x1, qa_hi[1], kl[2], kl[3]);
+        mma_f16(x2, qa_lo[1], kh[2], kh[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[nb][c] += x1[c] + x2[c];
       }
     }
   }
 
-  // ---- relative-key term, 64 keys at a time ------------------------------------------------------
+  // ---- relative-key term, 32 keys at a time ------------------------------------------------------
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int kh_cnt = min(64, nk16 - 64 * hh);  // keys in this half (multiple of 16), <= 0 -> nothing
-    if (kh_cnt > 0) {
-      // column j of the scratch <-> table row e0 + j, where  j = (l - l0) - (r - 64 hh) + (kh_cnt - 1)
-      const int e0 = l0 - 64 * hh + 128 - kh_cnt;
-      const int njb = (kh_cnt >> 3) + 2;
+  for (int qq = 0; qq < 4; ++qq) {
+    const int kq = min(32, nk16 - 32 * qq);  // keys in this chunk (16 or 32); <= 0 -> nothing
+    if (kq > 0) {
+      // column j of the scratch <-> table row e0 + j, where  j = (l - l0) - (r - 32 qq) + (kq - 1)
+      const int e0 = l0 - 32 * qq + 128 - kq;
+      const int njb = (kq >> 3) + 2;
       for (int jb = 0; jb < njb; ++jb) {
         float r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t eh[4], el[4];
@@ -169,22 +182,25 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
         mma_f16(r4, qa_hi[0], eh[0], eh[1]);
         mma_f16(r4, qa_hi[1], eh[2], eh[3]);
         if (THREE) {
+          float x1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, x2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           ldsm_x4(el, Es_lo + (e0 + jb * 8 + lm_row) * ATT_PITCH + lm_col);
-          mma_f16(r4, qa_hi[0], el[0], el[1]);
-          mma_f16(r4, qa_hi[1], el[2], el[3]);
-          mma_f16(r4, qa_lo[0], eh[0], eh[1]);
-          mma_f16(r4, qa_lo[1], eh[2], eh[3]);
+          mma_f16(x1, qa_hi[0], el[0], el[1]);
+          mma_f16(x2, qa_lo[0], eh[0], eh[1]);
+          mma_f16(x1, qa_hi[1], el[2], el[3]);
+          mma_f16(x2, qa_lo[1], eh[2], eh[3]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) r4[c] += x1[c] + x2[c];
         }
         *reinterpret_cast<float2*>(Rw + g * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[0], r4[1]);
         *reinterpret_cast<float2*>(Rw + (g + 8) * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[2], r4[3]);
       }
       __syncwarp();
 #pragma unroll
-      for (int nbl = 0; nbl < 8; ++nbl) {
-        const int nb = hh * 8 + nbl;
-        if (nbl * 8 < kh_cnt) {
-          const int rr = nbl * 8 + 2 * t;  // key index inside the half (first of this thread's two)
-          const int ca = g - rr + kh_cnt - 1, cb = g + 8 - rr + kh_cnt - 1;
+      for (int nbl = 0; nbl < 4; ++nbl) {
+        const int nb = qq * 4 + nbl;
+        if (nbl * 8 < kq) {
+          const int rr = nbl * 8 + 2 * t;  // key index inside the chunk (first of this thread's two)
+          const int ca = g - rr + kq - 1, cb = g + 8 - rr + kq - 1;
           s[nb][0] += Rw[g * ATT_RP + ca];
           s[nb][1] += Rw[g * ATT_RP + ca - 1];
           s[nb][2] += Rw[(g + 8) * ATT_RP + cb];
@@ -276,10 +292,13 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
   }
 }
 
-// Persistent kernel: grid = min(#SMs, batch * heads); work item w = chain * heads + head, taken round-robin.
-// The whole distance-embedding table of the layer stays in shared memory; K / V of the next item are
-// prefetched with cp.async while the current one is being computed (one __syncthreads per item).
-// THREE: 3-pass split (parity) or hi*hi only.
+__device__ __forceinline__ void att_group_barrier(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(ATT_GROUP_WARPS * 32) : "memory");
+}
+
+// Persistent kernel: grid <= #SMs; work item w = chain * heads + head.  Warp group `grp` of CTA `b` takes
+// items (b * 2 + grp), (b * 2 + grp) + 2 * grid, ...  The two groups only share the (read-only) distance
+// table; each has its own K / V buffer, bias row and named barrier.  THREE: 3-pass split or hi*hi only.
 template <bool THREE>
 __global__ void __launch_bounds__(ATT_WARPS * 32, 1)
 attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
@@ -290,39 +309,35 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* Es_hi = reinterpret_cast<__half*>(att_smem);
   __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
-  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // buffer b at kv0 + b * 4 * ATT_KV_HALVES
-  float* Rs = reinterpret_cast<float*>(kv0 + 2 * 4 * ATT_KV_HALVES);
-  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // bias buffer b at Bs0 + b * 128
+  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // group g: kv0 + g * 4 * ATT_KV_HALVES
+  float* Rs = reinterpret_cast<float*>(kv0 + ATT_GROUPS * 4 * ATT_KV_HALVES);
+  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // group g: Bs0 + g * 128
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, grp = warp / ATT_GROUP_WARPS, gwarp = warp % ATT_GROUP_WARPS;
   for (int i = tid; i < ATT_E_TABLE * 4; i += ATT_WARPS * 32) {
     const int r = i >> 2, c = (i & 3) * 8;
     cp_async16(Es_hi + r * ATT_PITCH + c, e_hi + (size_t)r * FD_HEAD_DIM + c);
     if (THREE) cp_async16(Es_lo + r * ATT_PITCH + c, e_lo + (size_t)r * FD_HEAD_DIM + c);
   }
-  int item = blockIdx.x;
-  if (item < n_items) {
-    const int chain = item / heads, head = item % heads;
-    att_stage_kv<THREE>(kv0, Bs0, qkv_hi, qkv_lo, key_bias, chain, head, row_start[chain], n_keys_arr[chain], n_pad, H);
-  }
-  float* Rw = Rs + warp * 16 * ATT_RP;
-  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
-    const int buf = it & 1;
-    cp_async_wait_all();
-    __syncthreads();  // item's K / V / bias (and, first time, E) visible; everyone is done with the other buffer
-    const int next = item + gridDim.x;
-    if (next < n_items) {
-      const int nc = next / heads, nh = next % heads;
-      att_stage_kv<THREE>(kv0 + (buf ^ 1) * 4 * ATT_KV_HALVES, Bs0 + (buf ^ 1) * 128, qkv_hi, qkv_lo, key_bias, nc, nh,
-                          row_start[nc], n_keys_arr[nc], n_pad, H);
-    }
-    const int chain = item / heads, head = item % heads;
-    const int n_rows = n_rows_arr[chain], l0 = warp * 16;
-    if (l0 < n_rows)
-      att_rows<THREE>(kv0 + buf * 4 * ATT_KV_HALVES, Es_hi, Es_lo, Rw, Bs0 + buf * 128, qkv_hi, qkv_lo,
-                      row_start[chain], l0, n_rows, n_keys_arr[chain], head, H, ctx_hi, ctx_lo);
-  }
   cp_async_wait_all();
+  __syncthreads();
+
+  __half* kv = kv0 + grp * 4 * ATT_KV_HALVES;
+  float* Bs = Bs0 + grp * 128;
+  float* Rw = Rs + warp * 16 * ATT_RP;
+  for (int item = blockIdx.x * ATT_GROUPS + grp; item < n_items; item += gridDim.x * ATT_GROUPS) {
+    const int chain = item / heads, head = item % heads;
+    const int r0 = row_start[chain], n_rows = n_rows_arr[chain], n_keys = n_keys_arr[chain];
+    const int l0 = gwarp * 16;
+    uint32_t qa_hi[2][4], qa_lo[2][4];
+    if (l0 < n_rows) att_load_q<THREE>(qa_hi, qa_lo, qkv_hi, qkv_lo, r0, l0, n_rows, head, H);
+    att_stage_kv<THREE>(kv, Bs, qkv_hi, qkv_lo, key_bias, chain, head, r0, n_keys, n_pad, H);
+    cp_async_wait_all();
+    att_group_barrier(grp);  // this item's K / V / bias are visible to the group
+    if (l0 < n_rows)
+      att_rows<THREE>(kv, Es_hi, Es_lo, Rw, Bs, qa_hi, qa_lo, r0, l0, n_rows, n_keys, head, H, ctx_hi, ctx_lo);
+    att_group_barrier(grp);  // everyone is done with the buffer before it is restaged
+  }
 }
 
 }  // namespace fd

@@ -146,6 +146,20 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
                ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// issue only; the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -186,10 +200,13 @@ struct TcCfg {
   static constexpr int W_BYTES = BN * TC_BK * 2;                        // BN * 128 B per plane
   static constexpr int PLANES = NPASS == 1 ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-  static constexpr int BUDGET = 200 * 1024;
+  // epilogue staging: one [32][36] fp32 transpose buffer per epilogue warp
+  static constexpr int EPI_PITCH = 36;
+  static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BUDGET = 227 * 1024 - EPI_BYTES - 2048;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large");
   static_assert(2 * BN <= (int)TC_TMEM_COLS, "two accumulators must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
@@ -305,64 +322,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM hands every thread one ROW of the accumulator (lane = row).  Writing global memory in
+    // that shape touches 32 different cache lines per instruction (ncu: the kernel was bound by it,
+    // long-scoreboard stalls behind scattered STG/LDG).  So each 32 x 32 chunk is transposed through
+    // a per-warp shared-memory buffer: afterwards 8 consecutive lanes cover 128 contiguous bytes of
+    // one row, and the bias / residual / GELU / fp16 hi-lo split run in that coalesced layout.
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     constexpr int COLS_PER_WARP = BN / (TC_EPI_WARPS / 4);
     static_assert(COLS_PER_WARP % 32 == 0, "column split of the epilogue warps");
+    constexpr int NCH = COLS_PER_WARP / 32;
+    constexpr int EP = Cfg::EPI_PITCH;
     const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 32 * EP;
+    const int lr = lane >> 3, lc = (lane & 7) * 4;  // coalesced layout: row inside a 4-row group, first column
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const int m0 = ((tile / n_blocks) * CL + crank) * TC_BM, n0 = (tile % n_blocks) * BN;
       if (!mbar_wait(&acc_full[acc], acc_phase)) { if (lane == 0) atomicExch(err_flag, 104); break; }
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      uint32_t v[32];
+      tmem_ld32_issue(t_row + (uint32_t)col_lo, v);
 #pragma unroll 1
-      for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
-        const size_t off = (size_t)row * N + n0 + c0;
-        float o[32];
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c0 = col_lo + ci * 32;
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
-          o[j] = fmaf(__uint_as_float(v[j]), out_scale, b4.x);
-          o[j + 1] = fmaf(__uint_as_float(v[j + 1]), out_scale, b4.y);
-          o[j + 2] = fmaf(__uint_as_float(v[j + 2]), out_scale, b4.z);
-          o[j + 3] = fmaf(__uint_as_float(v[j + 3]), out_scale, b4.w);
-          if (EPI == EPI_BIAS_RESID) {
-            const float4 r4 = *reinterpret_cast<const float4*>(resid + off + j);
-            o[j] += r4.x; o[j + 1] += r4.y; o[j + 2] += r4.z; o[j + 3] += r4.w;
-          }
-          if (EPI == EPI_BIAS_GELU) {
-            o[j] = gelu_erf(o[j]); o[j + 1] = gelu_erf(o[j + 1]);
-            o[j + 2] = gelu_erf(o[j + 2]); o[j + 3] = gelu_erf(o[j + 3]);
-          }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * EP + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (ci + 1 < NCH) {
+          tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), v);  // next chunk streams in under this chunk's math
+        } else {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);  // every TMEM read of this accumulator has completed
         }
-        if (C) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + lc);
+        float4 rs[8];
+        if (EPI == EPI_BIAS_RESID) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(C + off + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          for (int i = 0; i < 8; ++i)
+            rs[i] = *reinterpret_cast<const float4*>(resid + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + n0 + c0 + lc);
         }
-        if (c_hi) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t ph[4], pl[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __half h0 = __float2half_rn(o[j + 2 * q]), h1 = __float2half_rn(o[j + 2 * q + 1]);
-              const __half l0 = __float2half_rn(o[j + 2 * q] - __half2float(h0));
-              const __half l1 = __float2half_rn(o[j + 2 * q + 1] - __half2float(h1));
-              ph[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              pl[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + lr;
+          const float4 a = *reinterpret_cast<const float4*>(stg + r * EP + lc);
+          const size_t off = (size_t)(m0 + quad * 32 + r) * N + n0 + c0 + lc;
+          float o0 = fmaf(a.x, out_scale, b4.x), o1 = fmaf(a.y, out_scale, b4.y);
+          float o2 = fmaf(a.z, out_scale, b4.z), o3 = fmaf(a.w, out_scale, b4.w);
+          if (EPI == EPI_BIAS_RESID) { o0 += rs[i].x; o1 += rs[i].y; o2 += rs[i].z; o3 += rs[i].w; }
+          if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
+          if (C) *reinterpret_cast<float4*>(C + off) = make_float4(o0, o1, o2, o3);
+          if (c_hi) {
+            const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
+            uint2 ph;
+            ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+            *reinterpret_cast<uint2*>(c_hi + off) = ph;
+            if (c_lo) {
+              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+              const __half2 l01 = __floats2half2_rn(o0 - f01.x, o1 - f01.y), l23 = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
+              uint2 pl;
+              pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+              *reinterpret_cast<uint2*>(c_lo + off) = pl;
             }
-            *reinterpret_cast<uint4*>(c_hi + off + j) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            if (c_lo) *reinterpret_cast<uint4*>(c_lo + off + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           }
         }
+        __syncwarp();  // staging buffer is free for the next chunk
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);  // all epilogue threads arrive -> accumulator goes back to the MMA warp
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
