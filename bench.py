@@ -137,33 +137,58 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
-    """backbones/s of the reference's CPU path, from a bounded sample extrapolated to T steps."""
-    from oracle import forward as ofwd  # the one place bench.py may execute oracle/
+_CPU_MODEL = None
+
+
+def _cpu_model():
+    global _CPU_MODEL
+    if _CPU_MODEL is None:
+        from oracle import forward as ofwd  # the one place bench.py may execute oracle/
+        sd = synthetic.synthetic_state_dict(synthetic.PRODUCTION, seed=0)
+        _CPU_MODEL = ofwd.OracleModel(sd, ofwd.OracleConfig(**synthetic.PRODUCTION), [True] * 6).eval()
+    return _CPU_MODEL
+
+
+def _cpu_steps(sub, n_pad, T, start_t, steps, threads):
+    """seconds per reverse step of the oracle port on `threads` host threads (1 untimed warm-up step)."""
     from oracle import loop as oloop
     from oracle import schedules as osched
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = synthetic.synthetic_state_dict(synthetic.PRODUCTION, seed=0)
-    model = ofwd.OracleModel(sd, ofwd.OracleConfig(**synthetic.PRODUCTION), [True] * 6).eval()
-    stride = max(1, len(lengths) // chains)
-    sub = [lengths[i] for i in range(0, len(lengths), stride)][:chains]
+    torch.set_num_threads(threads)
+    model = _cpu_model()
     betas = osched.betas_for("cosine", T)
     g = torch.Generator().manual_seed(SEED)
     x = oloop.wrap(torch.randn(len(sub), n_pad, 6, generator=g))
-    t_hi = start_t
-    oloop.p_sample_loop(model, sub, x, T, betas, [True] * 6, start_t=1, wrap_all=wrap_all)  # warm-up step
+    x = oloop.wrap(oloop.p_sample(model, x, torch.full((len(sub),), start_t - 1, dtype=torch.long), sub, betas))
     t0 = time.perf_counter()
-    # per-step cost does not depend on t: time `steps` reverse steps, extrapolate to the full loop
-    x1 = x
-    for k in range(steps):
-        x1 = oloop.p_sample(model, x1, torch.full((len(sub),), t_hi - 1 - k, dtype=torch.long), sub, betas)
-        x1 = oloop.wrap(x1)
-    dt = (time.perf_counter() - t0) / steps
+    for k in range(steps):  # per-step cost does not depend on t
+        x = oloop.wrap(oloop.p_sample(model, x, torch.full((len(sub),), start_t - 2 - k, dtype=torch.long), sub, betas))
+    return (time.perf_counter() - t0) / steps
+
+
+_BEST_THREADS = None
+
+
+def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
+    """
+    backbones/s of the reference's CPU path from a bounded sample: `chains` chains taken evenly from the
+    workload's length mix, `steps` reverse steps timed after one warm-up, extrapolated to the full loop.
+    torch's CPU kernels do not scale to every core count, so the thread count is chosen by a one-step
+    probe over {all cores, 64, 32, 16} and the best one is used ("all the host threads it can use").
+    """
+    global _BEST_THREADS
+    cores = os.cpu_count() or 1
+    stride = max(1, len(lengths) // chains)
+    sub = [lengths[i] for i in range(0, len(lengths), stride)][:chains]
+    if _BEST_THREADS is None:
+        cands = sorted({c for c in (cores, 64, 32, 16) if c <= cores}, reverse=True)
+        probe = {c: _cpu_steps(sub, n_pad, T, start_t, 1, c) for c in cands}
+        _BEST_THREADS = min(probe, key=probe.get)
+    dt = _cpu_steps(sub, n_pad, T, start_t, steps, _BEST_THREADS)
     rate = len(sub) / (dt * start_t)
     sample = (f"{len(sub)} chains (every {stride}-th of the workload's lengths, sum len {sum(sub)}), {steps} reverse steps "
-              f"timed after 1 warm-up at {dt:.3f} s/step, extrapolated x{start_t} steps")
-    return rate, cores, sample, dt
+              f"timed after 1 warm-up at {dt:.3f} s/step on {_BEST_THREADS} threads (best of a 1-step probe; box has {cores} "
+              f"cores), extrapolated x{start_t} steps")
+    return rate, _BEST_THREADS, sample, dt
 
 
 # ------------------------------------------------------------------------------------------------
