@@ -33,16 +33,16 @@ namespace fd {
 constexpr int ATT_GROUP_WARPS = 8;  // 8 warps x 16 query rows = the whole chain (n <= 128)
 constexpr int ATT_GROUPS = 2;       // independent warp groups per CTA
 constexpr int ATT_WARPS = ATT_GROUP_WARPS * ATT_GROUPS;
-constexpr int ATT_PITCH = 40;     // halves per smem row (32 + 8 pad -> conflict-free ldmatrix)
-constexpr int ATT_RP = 72;        // fp32 scratch pitch (== 8 mod 32; >= 32 + 16 columns)
+constexpr int ATT_PITCH = 32;     // halves per smem row: unpadded 64-byte rows, 16-byte chunks XOR-swizzled (att_sw)
+constexpr int ATT_RP = 56;        // fp32 scratch pitch (== 24 mod 32: conflict-free float2 stores; >= 32 + 16 columns)
 constexpr int ATT_E_TABLE = 256;  // rows of the padded per-layer table (255 real + 1 zero row)
 constexpr int ATT_KV_HALVES = 128 * ATT_PITCH;  // one K or V plane of one work item
 
 constexpr size_t att_smem_bytes() {
   return (size_t)2 * ATT_E_TABLE * ATT_PITCH * 2      // E hi/lo, whole table, resident for the kernel's life
-         + (size_t)ATT_GROUPS * 4 * ATT_KV_HALVES * 2   // per group {K hi, K lo, V hi, V lo}
-         + (size_t)ATT_WARPS * 16 * ATT_RP * 4          // R scratch
-         + (size_t)ATT_GROUPS * 128 * 4;                // per group key bias
+         + (size_t)ATT_GROUPS * 2 * 4 * ATT_KV_HALVES * 2   // per group, double-buffered {K hi, K lo, V hi, V lo}
+         + (size_t)ATT_WARPS * 16 * ATT_RP * 4              // R scratch
+         + (size_t)ATT_GROUPS * 2 * 128 * 4;                // per group, double-buffered key bias
 }
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -68,6 +68,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Offset (in halves) of the 16-byte chunk `c` (0..3) of row `r` in a [rows][32 halves] tile.  Rows are 64 bytes,
+// unpadded; the chunk index is XOR-ed with bits 1-2 of the row, so the eight rows of one ldmatrix 8x8 matrix
+// (same logical chunk, consecutive rows) land in eight different 16-byte bank groups.
+__device__ __forceinline__ int att_sw(int r, int c) { return r * ATT_PITCH + ((c ^ ((r >> 1) & 3)) << 3); }
+
 // (x0, x1) -> packed fp16 hi and lo words
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
@@ -88,7 +93,7 @@ __device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const _
   __half* Vs_hi = buf + 2 * ATT_KV_HALVES; __half* Vs_lo = buf + 3 * ATT_KV_HALVES;
   for (int i = gtid; i < nk16 * 4; i += ATT_GROUP_WARPS * 32) {
     const int r = i >> 2, c = (i & 3) * 8;  // 8 halves = 16 bytes
-    const int so = r * ATT_PITCH + c;
+    const int so = att_sw(r, i & 3);
     if (r < n_keys) {
       const size_t off = (size_t)(r0 + r) * ld + head * FD_HEAD_DIM + c;
       cp_async16(Ks_hi + so, qkv_hi + off + H);
@@ -141,7 +146,7 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
   const int nk16 = (n_keys + 15) & ~15;
 
   // B-operand row address pattern of ldmatrix.x4 over a [8 rows][32 halves] tile: lane -> (row, 8-half column block)
-  const int lm_row = lane & 7, lm_col = (lane >> 3) * 8;
+  const int lm_row = lane & 7, lm_c = lane >> 3;
 
   // ---- S = Q K^T ---------------------------------------------------------------------------------
   float s[16][4];
@@ -151,18 +156,18 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
     s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
     if (nb < nnb) {
       uint32_t kh[4], kl[4];
-      ldsm_x4(kh, Ks_hi + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
+      ldsm_x4(kh, Ks_hi + att_sw(nb * 8 + lm_row, lm_c));
       mma_f16(s[nb], qa_hi[0], kh[0], kh[1]);
       mma_f16(s[nb], qa_hi[1], kh[2], kh[3]);
-      if (THREE) {  // the two correction products get their own accumulators: three short independent chains
-        float x1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, x2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        ldsm_x4(kl, Ks_lo + (nb * 8 + lm_row) * ATT_PITCH + lm_col);
-        mma_f16(x1, qa_hi[0], kl[0], kl[1]);
-        mma_f16(x2, qa_lo[0], kh[0], kh[1]);
-        mma_f16(x1, qa_hi[1], kl[2], kl[3]);
-        mma_f16(x2, qa_lo[1], kh[2], kh[3]);
+      if (THREE) {  // the correction products get their own accumulator: two independent chains per block
+        float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        ldsm_x4(kl, Ks_lo + att_sw(nb * 8 + lm_row, lm_c));
+        mma_f16(x, qa_hi[0], kl[0], kl[1]);
+        mma_f16(x, qa_lo[0], kh[0], kh[1]);
+        mma_f16(x, qa_hi[1], kl[2], kl[3]);
+        mma_f16(x, qa_lo[1], kh[2], kh[3]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s[nb][c] += x1[c] + x2[c];
+        for (int c = 0; c < 4; ++c) s[nb][c] += x[c];
       }
     }
   }
@@ -178,18 +183,18 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
       for (int jb = 0; jb < njb; ++jb) {
         float r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         uint32_t eh[4], el[4];
-        ldsm_x4(eh, Es_hi + (e0 + jb * 8 + lm_row) * ATT_PITCH + lm_col);
+        ldsm_x4(eh, Es_hi + att_sw(e0 + jb * 8 + lm_row, lm_c));
         mma_f16(r4, qa_hi[0], eh[0], eh[1]);
         mma_f16(r4, qa_hi[1], eh[2], eh[3]);
         if (THREE) {
-          float x1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, x2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          ldsm_x4(el, Es_lo + (e0 + jb * 8 + lm_row) * ATT_PITCH + lm_col);
-          mma_f16(x1, qa_hi[0], el[0], el[1]);
-          mma_f16(x2, qa_lo[0], eh[0], eh[1]);
-          mma_f16(x1, qa_hi[1], el[2], el[3]);
-          mma_f16(x2, qa_lo[1], eh[2], eh[3]);
+          float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          ldsm_x4(el, Es_lo + att_sw(e0 + jb * 8 + lm_row, lm_c));
+          mma_f16(x, qa_hi[0], el[0], el[1]);
+          mma_f16(x, qa_lo[0], eh[0], eh[1]);
+          mma_f16(x, qa_hi[1], el[2], el[3]);
+          mma_f16(x, qa_lo[1], eh[2], eh[3]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) r4[c] += x1[c] + x2[c];
+          for (int c = 0; c < 4; ++c) r4[c] += x[c];
         }
         *reinterpret_cast<float2*>(Rw + g * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[0], r4[1]);
         *reinterpret_cast<float2*>(Rw + (g + 8) * ATT_RP + jb * 8 + 2 * t) = make_float2(r4[2], r4[3]);
@@ -246,7 +251,7 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
   for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.0f;
   const int nkb = nk16 >> 4;
   // ldmatrix.x4.trans over a [16 keys][16 d] tile: lane -> (key row, d column block)
-  const int vt_row = (lane & 7) + ((lane >> 3) & 1) * 8, vt_col = (lane >> 4) * 8;
+  const int vt_row = (lane & 7) + ((lane >> 3) & 1) * 8, vt_c = lane >> 4;
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
     if (kb < nkb) {
@@ -258,11 +263,11 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
 #pragma unroll
       for (int dp = 0; dp < 2; ++dp) {
         uint32_t vh[4], vl[4];
-        ldsm_x4_t(vh, Vs_hi + (kb * 16 + vt_row) * ATT_PITCH + dp * 16 + vt_col);
+        ldsm_x4_t(vh, Vs_hi + att_sw(kb * 16 + vt_row, dp * 2 + vt_c));
         mma_f16(o[2 * dp], p_hi, vh[0], vh[1]);
         mma_f16(o[2 * dp + 1], p_hi, vh[2], vh[3]);
         if (THREE) {
-          ldsm_x4_t(vl, Vs_lo + (kb * 16 + vt_row) * ATT_PITCH + dp * 16 + vt_col);
+          ldsm_x4_t(vl, Vs_lo + att_sw(kb * 16 + vt_row, dp * 2 + vt_c));
           mma_f16(o[2 * dp], p_hi, vl[0], vl[1]);
           mma_f16(o[2 * dp + 1], p_hi, vl[2], vl[3]);
           mma_f16(o[2 * dp], p_lo, vh[0], vh[1]);
@@ -309,35 +314,53 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* Es_hi = reinterpret_cast<__half*>(att_smem);
   __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
-  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // group g: kv0 + g * 4 * ATT_KV_HALVES
-  float* Rs = reinterpret_cast<float*>(kv0 + ATT_GROUPS * 4 * ATT_KV_HALVES);
-  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // group g: Bs0 + g * 128
+  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // group g, buffer b: kv0 + (g * 2 + b) * 4 * ATT_KV_HALVES
+  float* Rs = reinterpret_cast<float*>(kv0 + ATT_GROUPS * 2 * 4 * ATT_KV_HALVES);
+  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // group g, buffer b: Bs0 + (g * 2 + b) * 128
 
   const int tid = threadIdx.x, warp = tid >> 5, grp = warp / ATT_GROUP_WARPS, gwarp = warp % ATT_GROUP_WARPS;
   for (int i = tid; i < ATT_E_TABLE * 4; i += ATT_WARPS * 32) {
-    const int r = i >> 2, c = (i & 3) * 8;
-    cp_async16(Es_hi + r * ATT_PITCH + c, e_hi + (size_t)r * FD_HEAD_DIM + c);
-    if (THREE) cp_async16(Es_lo + r * ATT_PITCH + c, e_lo + (size_t)r * FD_HEAD_DIM + c);
+    const int r = i >> 2;
+    cp_async16(Es_hi + att_sw(r, i & 3), e_hi + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
+    if (THREE) cp_async16(Es_lo + att_sw(r, i & 3), e_lo + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
   }
   cp_async_wait_all();
   __syncthreads();
 
-  __half* kv = kv0 + grp * 4 * ATT_KV_HALVES;
-  float* Bs = Bs0 + grp * 128;
+  __half* kvg = kv0 + grp * 2 * 4 * ATT_KV_HALVES;
+  float* Bsg = Bs0 + grp * 2 * 128;
   float* Rw = Rs + warp * 16 * ATT_RP;
-  for (int item = blockIdx.x * ATT_GROUPS + grp; item < n_items; item += gridDim.x * ATT_GROUPS) {
-    const int chain = item / heads, head = item % heads;
-    const int r0 = row_start[chain], n_rows = n_rows_arr[chain], n_keys = n_keys_arr[chain];
+  const int stride = gridDim.x * ATT_GROUPS;
+  int item = blockIdx.x * ATT_GROUPS + grp;
+  // item metadata is read one item ahead so its L2 latency never sits on the critical path
+  int chain = 0, head = 0, r0 = 0, n_rows = 0, n_keys = 0;
+  if (item < n_items) {
+    chain = item / heads; head = item % heads;
+    r0 = row_start[chain]; n_rows = n_rows_arr[chain]; n_keys = n_keys_arr[chain];
+    att_stage_kv<THREE>(kvg, Bsg, qkv_hi, qkv_lo, key_bias, chain, head, r0, n_keys, n_pad, H);
+  }
+  for (int it = 0; item < n_items; item += stride, ++it) {
+    const int buf = it & 1;
     const int l0 = gwarp * 16;
     uint32_t qa_hi[2][4], qa_lo[2][4];
     if (l0 < n_rows) att_load_q<THREE>(qa_hi, qa_lo, qkv_hi, qkv_lo, r0, l0, n_rows, head, H);
-    att_stage_kv<THREE>(kv, Bs, qkv_hi, qkv_lo, key_bias, chain, head, r0, n_keys, n_pad, H);
+    const int nitem = item + stride;
+    int nchain = 0, nhead = 0, nr0 = 0, nn_rows = 0, nn_keys = 0;
+    if (nitem < n_items) {
+      nchain = nitem / heads; nhead = nitem % heads;
+      nr0 = row_start[nchain]; nn_rows = n_rows_arr[nchain]; nn_keys = n_keys_arr[nchain];
+    }
     cp_async_wait_all();
-    att_group_barrier(grp);  // this item's K / V / bias are visible to the group
+    att_group_barrier(grp);  // this item's K / V / bias are visible; everyone has left the other buffer
+    if (nitem < n_items)     // stage the next item under this item's math
+      att_stage_kv<THREE>(kvg + (buf ^ 1) * 4 * ATT_KV_HALVES, Bsg + (buf ^ 1) * 128, qkv_hi, qkv_lo, key_bias, nchain,
+                          nhead, nr0, nn_keys, n_pad, H);
     if (l0 < n_rows)
-      att_rows<THREE>(kv, Es_hi, Es_lo, Rw, Bs, qa_hi, qa_lo, r0, l0, n_rows, n_keys, head, H, ctx_hi, ctx_lo);
-    att_group_barrier(grp);  // everyone is done with the buffer before it is restaged
+      att_rows<THREE>(kvg + buf * 4 * ATT_KV_HALVES, Es_hi, Es_lo, Rw, Bsg + buf * 128, qa_hi, qa_lo, r0, l0, n_rows,
+                      n_keys, head, H, ctx_hi, ctx_lo);
+    chain = nchain; head = nhead; r0 = nr0; n_rows = nn_rows; n_keys = nn_keys;
   }
+  cp_async_wait_all();
 }
 
 }  // namespace fd

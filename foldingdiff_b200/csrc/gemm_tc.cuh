@@ -6,9 +6,13 @@
 //     warps 2..9 = epilogue (tcgen05.ld -> registers -> bias / residual / GELU -> global); two warps
 //     share each TMEM lane quadrant and split the tile's columns
 //   * two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i + 1
-//   * thread-block clusters of 2 along M: the two CTAs work on vertically adjacent row blocks of the
-//     same column block, each fetches HALF of the weight tile and TMA-multicasts it to both, which cuts
-//     the L2 -> SM operand traffic this kernel is bound by (ncu: ~7 TB/s at 35% MMA issue) by 30%
+//   * CTA pairs (cta_group::2, default): the two CTAs of a 2-cluster sit on the two SMs of a TPC and
+//     compute ONE 256 x BN tile - each SM stages its own 128 rows of A and only HALF of the weight
+//     tile, the MMA (issued by the leader CTA) reads both halves.  ncu on the 1-CTA kernel showed it
+//     shared-memory-bandwidth bound (operand reads 107 B/clk + TMA writes 71 + epilogue staging 28
+//     against 128 B/clk/SM, tensor pipe capped at ~60%); the pair halves the B-operand traffic per SM
+//     and the smaller stage buys a third pipeline stage.
+//   * (A/B fallback) independent CTAs in a 2-cluster sharing the weight tile by TMA multicast
 //
 // Precision.  The parity gate of this project is 1e-4 max-abs on fp32 angle tensors, which single
 // pass fp16/bf16/tf32 operands do not meet.  FD_GEMM_TC_3X therefore runs
@@ -106,6 +110,26 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
+// cta_group::2 load: issued by BOTH CTAs of the pair for their own smem; the byte count is reported to
+// the LEADER's mbarrier (peer bit of the shared-window address cleared, as CUTLASS SM100_TMA_2SM_LOAD).
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  const uint64_t policy = 0x1000000000000000ull;  // EVICT_NORMAL
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -124,6 +148,28 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
@@ -187,17 +233,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = bn.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int bn) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int bn, int m = TC_BM) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool PAIR = false>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;                     // 16 KB per plane
-  static constexpr int W_BYTES = BN * TC_BK * 2;                        // BN * 128 B per plane
+  static constexpr int W_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;      // rows of W this CTA stages, 128 B each
   static constexpr int PLANES = NPASS == 1 ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
   // epilogue staging: one [32][36] fp32 transpose buffer per epilogue warp
@@ -212,14 +258,15 @@ struct TcCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 };
 
-template <int BN, int NPASS, int EPI, int CL>
+template <int BN, int NPASS, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const float* __restrict__ bias, const float* __restrict__ resid, float* __restrict__ C,
                __half* __restrict__ c_hi, __half* __restrict__ c_lo, int M, int N, int K,
                float out_scale, int* __restrict__ err_flag) {
-  using Cfg = TcCfg<BN, NPASS>;
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
+  using Cfg = TcCfg<BN, NPASS, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -238,13 +285,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
+  const bool leader = !PAIR || crank == 0;  // in a pair only the leader CTA issues MMAs
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * TC_EPI_WARPS); }
+    // PAIR: `full` and `acc_empty` are only used in the leader (they collect both CTAs' bytes / arrivals);
+    // `empty` and `acc_full` exist in both CTAs and are signalled by the leader's multicast commits.
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PAIR ? 1 : CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * 32 * TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS); else tmem_alloc(tmem_slot, TC_TMEM_COLS); }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_w_hi);
     if (NPASS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_lo); }
@@ -266,11 +316,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // the stage is free once the MMA warps of ALL CTAs in the cluster have drained it
           if (!mbar_wait(&empty[stage], phase ^ 1)) { atomicExch(err_flag, 101); ok = false; break; }
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* w_hi = s + Cfg::PLANES * Cfg::A_BYTES;
+          uint8_t* w_lo = w_hi + Cfg::W_BYTES;
+          if (PAIR) {
+            // both CTAs stage their own 128 rows of A and their half of the weight tile; every byte is
+            // accounted on the leader's barrier, which expects the pair's total
+            if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(s, &map_a_hi, &full[stage], kb * TC_BK, m0);
+            tma_load_2d_2sm(w_hi, &map_w_hi, &full[stage], kb * TC_BK, n0 + crank * (BN / 2));
+            if (NPASS > 1) {
+              tma_load_2d_2sm(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
+              tma_load_2d_2sm(w_lo, &map_w_lo, &full[stage], kb * TC_BK, n0 + crank * (BN / 2));
+            }
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(s, &map_a_hi, &full[stage], kb * TC_BK, m0);
           if (NPASS > 1) tma_load_2d(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
-          uint8_t* w_hi = s + Cfg::PLANES * Cfg::A_BYTES;
-          uint8_t* w_lo = w_hi + Cfg::W_BYTES;
           if (CL == 1) {
             tma_load_2d(w_hi, &map_w_hi, &full[stage], kb * TC_BK, n0);
             if (NPASS > 1) tma_load_2d(w_lo, &map_w_lo, &full[stage], kb * TC_BK, n0);
@@ -286,8 +349,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, PAIR ? 2 * TC_BM : TC_BM);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
@@ -305,16 +368,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint32_t koff = k * TC_UMMA_K * 2;  // bytes inside the 128-byte swizzle row
             const uint64_t da_hi = umma_desc_sw128(a_hi + koff), dw_hi = umma_desc_sw128(w_hi + koff);
-            umma_f16(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_f16_2sm(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (NPASS > 1) {
               const uint64_t da_lo = umma_desc_sw128(a_lo + koff), dw_lo = umma_desc_sw128(w_lo + koff);
-              umma_f16(d_tmem, da_hi, dw_lo, idesc, 1u);
-              umma_f16(d_tmem, da_lo, dw_hi, idesc, 1u);
+              if (PAIR) { umma_f16_2sm(d_tmem, da_hi, dw_lo, idesc, 1u); umma_f16_2sm(d_tmem, da_lo, dw_hi, idesc, 1u); }
+              else { umma_f16(d_tmem, da_hi, dw_lo, idesc, 1u); umma_f16(d_tmem, da_lo, dw_hi, idesc, 1u); }
             }
           }
-          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above retire
-          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], kMask);
-          if (kb == k_blocks - 1) umma_commit(&acc_full[acc]);
+          // frees this smem stage (in every CTA that stages into it) once the MMAs above retire
+          if (PAIR) umma_commit_2sm_mc(&empty[stage], kMask);
+          else if (CL == 1) umma_commit(&empty[stage]);
+          else umma_commit_mc(&empty[stage], kMask);
+          if (kb == k_blocks - 1) { if (PAIR) umma_commit_2sm_mc(&acc_full[acc], kMask); else umma_commit(&acc_full[acc]); }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -355,8 +421,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (ci + 1 < NCH) {
           tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), v);  // next chunk streams in under this chunk's math
         } else {
-          tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);  // every TMEM read of this accumulator has completed
+          tc_fence_before();  // every TMEM read of this accumulator has completed
+          if (PAIR && !leader) mbar_arrive_remote(&acc_empty[acc], 0);  // the leader's MMA warp owns the barrier
+          else mbar_arrive(&acc_empty[acc]);
         }
         const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + lc);
         float4 rs[8];
@@ -400,7 +467,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (CL > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS); else tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -566,22 +633,25 @@ inline int tc_check_error() {
   return v;
 }
 
-// FOLDINGDIFF_B200_TC_CLUSTER=1 disables the 2-CTA multicast clusters (A/B switch for profiling).
-inline int tc_cluster_size() {
-  static int cl = -1;
-  if (cl < 0) {
-    const char* e = getenv("FOLDINGDIFF_B200_TC_CLUSTER");
-    cl = (e && e[0] == '1') ? 1 : 2;
+// FOLDINGDIFF_B200_TC_MODE: "pair" (default: cta_group::2 CTA pairs), "mcast" (independent CTAs of a
+// 2-cluster sharing W by TMA multicast), "single" (no cluster).  A/B switch for profiling.
+inline int tc_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FOLDINGDIFF_B200_TC_MODE");
+    mode = 2;
+    if (e && e[0] == 'm') mode = 1;
+    if (e && e[0] == 's') mode = 0;
   }
-  return cl;
+  return mode;
 }
 
-template <int BN, int NPASS, int EPI, int CL>
+template <int BN, int NPASS, int EPI, int CL, bool PAIR>
 int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
                  TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
-  using Cfg = TcCfg<BN, NPASS>;
+  using Cfg = TcCfg<BN, NPASS, PAIR>;
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BN, NPASS, EPI, CL>;
+  auto kern = tc_gemm_kernel<BN, NPASS, EPI, CL, PAIR>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
     configured = true;
@@ -613,9 +683,11 @@ int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const f
 template <int BN, int NPASS, int EPI>
 int tc_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
               TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
-  if (tc_cluster_size() == 2 && M % (2 * TC_BM) == 0)
-    return tc_launch_cl<BN, NPASS, EPI, 2>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
-  return tc_launch_cl<BN, NPASS, EPI, 1>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  if (M % (2 * TC_BM) == 0 && tc_mode() == 2)
+    return tc_launch_cl<BN, NPASS, EPI, 2, true>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  if (M % (2 * TC_BM) == 0 && tc_mode() == 1)
+    return tc_launch_cl<BN, NPASS, EPI, 2, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+  return tc_launch_cl<BN, NPASS, EPI, 1, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
 }
 
 template <int BN, int NPASS>
