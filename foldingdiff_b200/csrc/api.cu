@@ -226,6 +226,17 @@ int project(fd_handle* H, int cat, int epi, const float* A, const float* W, cons
   return FD_OK;
 }
 
+// Fused projection + residual + LayerNorm on the tensor-core path (gemm_tc.cuh: tc_gemm_ln_kernel).
+int project_ln(fd_handle* H, int cat, const fd::TcPlane* a_tc, const fd::TcWeight* tw, const float* bias,
+               const float* resid, const float* g, const float* b, float* out, fd::TcPlane* o_tc, int K, cudaStream_t st) {
+  ProfScope ps(H, cat, st);
+  int rc = fd::tc_gemm_ln(H->gemm_mode, a_tc, tw, bias, resid, g, b, H->d.ln_eps, H->tmp, out, o_tc, H->rows_pad, K,
+                          H->sm_count, st);
+  if (rc != 0) return fail(FD_ERR_CUDA, "fused GEMM+LayerNorm launch failed (%d)", rc);
+  H->launches++;
+  return FD_OK;
+}
+
 // The noise-predictor forward on the current batch: leaves gelu(dense1(h_L)) in H->tmp.
 // fp32 mode: every tensor fp32, CUDA-core kernels.  tc modes: the residual stream (h, a, tmp) stays
 // fp32; GEMM operands travel as fp16 hi / lo planes written by the producing kernel's epilogue
@@ -242,17 +253,28 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
     if (rc) return rc;
     if (tcm) launch_attention_mma(H, w, st);
     else launch_attention(H, w.dist, st);
-    rc = project(H, CAT_GEMM_OUT, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp,
-                 Hd, Hd, &H->tc.ctx, nullptr, st);
-    if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, tcm ? H->h : nullptr, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
+    const bool fuse = tcm && fd::tc_gemm_ln_supported(&w.to, H->rows_pad);
+    if (fuse) {
+      rc = project_ln(H, CAT_GEMM_OUT, &H->tc.ctx, &w.to, w.b_o, H->h, w.ln1_g, w.ln1_b, H->a, &H->tc.a, Hd, st);
+      if (rc) return rc;
+    } else {
+      rc = project(H, CAT_GEMM_OUT, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp,
+                   Hd, Hd, &H->tc.ctx, nullptr, st);
+      if (rc) return rc;
+      launch_ln<VPL>(H, H->tmp, tcm ? H->h : nullptr, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
+    }
     rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, tcm ? nullptr : H->inter,
                  I, Hd, &H->tc.a, tcm ? &H->tc.inter : nullptr, st);
     if (rc) return rc;
-    rc = project(H, CAT_GEMM_FFN2, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a, H->tmp,
-                 Hd, I, &H->tc.inter, nullptr, st);
-    if (rc) return rc;
-    launch_ln<VPL>(H, H->tmp, tcm ? H->a : nullptr, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
+    if (fuse) {
+      rc = project_ln(H, CAT_GEMM_FFN2, &H->tc.inter, &w.to2, w.b_o2, H->a, w.ln2_g, w.ln2_b, H->h, &H->tc.h, I, st);
+      if (rc) return rc;
+    } else {
+      rc = project(H, CAT_GEMM_FFN2, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a,
+                   H->tmp, Hd, I, &H->tc.inter, nullptr, st);
+      if (rc) return rc;
+      launch_ln<VPL>(H, H->tmp, tcm ? H->a : nullptr, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
+    }
   }
   return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, &H->td1, H->b_d1, nullptr, H->tmp, Hd, Hd,
                  &H->tc.h, nullptr, st);

@@ -112,9 +112,11 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
 }
 // cta_group::2 load: issued by BOTH CTAs of the pair for their own smem; the byte count is reported to
 // the LEADER's mbarrier (peer bit of the shared-window address cleared, as CUTLASS SM100_TMA_2SM_LOAD).
-__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+constexpr uint64_t TC_EVICT_FIRST = 0x12F0000000000000ull;  // streamed once (activation planes)
+constexpr uint64_t TC_EVICT_LAST = 0x14F0000000000000ull;   // re-read by every CTA (weights)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                uint64_t policy) {
   const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
-  const uint64_t policy = 0x1000000000000000ull;  // EVICT_NORMAL
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
@@ -264,7 +266,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const float* __restrict__ bias, const float* __restrict__ resid, float* __restrict__ C,
                __half* __restrict__ c_hi, __half* __restrict__ c_lo, int M, int N, int K,
-               float out_scale, int* __restrict__ err_flag) {
+               float out_scale, int* __restrict__ err_flag, unsigned long long a_policy) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
   using Cfg = TcCfg<BN, NPASS, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -322,11 +324,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // both CTAs stage their own 128 rows of A and their half of the weight tile; every byte is
             // accounted on the leader's barrier, which expects the pair's total
             if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(s, &map_a_hi, &full[stage], kb * TC_BK, m0);
-            tma_load_2d_2sm(w_hi, &map_w_hi, &full[stage], kb * TC_BK, n0 + crank * (BN / 2));
+            tma_load_2d_2sm(s, &map_a_hi, &full[stage], kb * TC_BK, m0, a_policy);
+            tma_load_2d_2sm(w_hi, &map_w_hi, &full[stage], kb * TC_BK, n0 + crank * (BN / 2), TC_EVICT_LAST);
             if (NPASS > 1) {
-              tma_load_2d_2sm(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0);
-              tma_load_2d_2sm(w_lo, &map_w_lo, &full[stage], kb * TC_BK, n0 + crank * (BN / 2));
+              tma_load_2d_2sm(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0, a_policy);
+              tma_load_2d_2sm(w_lo, &map_w_lo, &full[stage], kb * TC_BK, n0 + crank * (BN / 2), TC_EVICT_LAST);
             }
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             continue;
@@ -468,6 +470,269 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS); else tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fused projection + residual + LayerNorm (BertSelfOutput / BertOutput):
+//     out = LN(A W^T + bias + resid) * gamma + beta        and its fp16 hi / lo planes
+// CTA pairs only.  N = NH * 192 <= 384 is the whole hidden size, so each CTA of the pair owns COMPLETE
+// rows (its 128 rows x N columns live in its TMEM as NH accumulators of 192 columns) and the row
+// statistics never leave the CTA.  Epilogue, per tile:
+//   phase A  TMEM -> smem transpose -> x' = acc * scale + bias + resid (coalesced), x' parked in a
+//            global scratch that stays in L2, per-row sum / sum-of-squares accumulated in registers;
+//            the accumulator is released as soon as its last column has been read
+//   barrier  (named, epilogue warps only) + combine the two column halves through shared memory
+//   phase B  x' re-read (L2), normalised, written as fp32 + hi / lo planes - this overlaps the next
+//            tile's MMAs.
+// It removes the standalone LayerNorm kernel's HBM round trip - but see tc_gemm_ln_supported(): as measured it
+// is latency-bound and loses to the two-kernel path, so it is opt-in.
+template <int NH, int NPASS>
+struct TcLnCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int W_BYTES = NH * 96 * TC_BK * 2;     // this CTA's share of the weight tile, per plane
+  static constexpr int PLANES = NPASS == 1 ? 1 : 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+  static constexpr int EPI_PITCH = 36;
+  static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int STAT_BYTES = 2 * TC_EPI_WARPS * 32 * 2 * 4;  // double-buffered [warp][row][sum, sumsq]
+  static constexpr int BUDGET = 227 * 1024 - EPI_BYTES - STAT_BYTES - 2048;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + STAT_BYTES;
+  static constexpr uint32_t TMEM_COLS = NH == 1 ? 256 : 512;
+  static_assert(STAGES >= 2, "tile too large");
+};
+
+template <int NH, int NPASS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float ln_eps, float* __restrict__ scratch, float* __restrict__ out,
+                  __half* __restrict__ o_hi, __half* __restrict__ o_lo, int M, int K, float out_scale,
+                  int* __restrict__ err_flag) {
+  using Cfg = TcLnCfg<NH, NPASS>;
+  constexpr int N = NH * 192;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;   // [1]
+  uint64_t* acc_empty = acc_full + 1;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = M / (2 * TC_BM), k_blocks = K / TC_BK;
+  const int crank = (int)cluster_rank();
+  const bool leader = crank == 0;
+  const int tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 2 * 32 * TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_w_hi);
+    if (NPASS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_lo); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
+        const int m0 = (tile * 2 + crank) * TC_BM;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          if (!mbar_wait(&empty[stage], phase ^ 1)) { atomicExch(err_flag, 201); ok = false; break; }
+          uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* w_hi = s + Cfg::PLANES * Cfg::A_BYTES;
+          uint8_t* w_lo = w_hi + Cfg::W_BYTES;
+          if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(s, &map_a_hi, &full[stage], kb * TC_BK, m0, TC_EVICT_FIRST);
+          if (NPASS > 1) tma_load_2d_2sm(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0, TC_EVICT_FIRST);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {  // column half h: this CTA stages 96 of its 192 weight rows
+            tma_load_2d_2sm(w_hi + h * 96 * 128, &map_w_hi, &full[stage], kb * TC_BK, h * 192 + crank * 96, TC_EVICT_LAST);
+            if (NPASS > 1)
+              tma_load_2d_2sm(w_lo + h * 96 * 128, &map_w_lo, &full[stage], kb * TC_BK, h * 192 + crank * 96, TC_EVICT_LAST);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(192, 2 * TC_BM);
+      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
+        if (!mbar_wait(acc_empty, acc_phase ^ 1)) { atomicExch(err_flag, 202); break; }
+        tc_fence_after();
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          if (!mbar_wait(&full[stage], phase)) { atomicExch(err_flag, 203); ok = false; break; }
+          tc_fence_after();
+          const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_hi = s, a_lo = s + Cfg::A_BYTES;
+          const uint32_t w_hi = s + Cfg::PLANES * Cfg::A_BYTES, w_lo = w_hi + Cfg::W_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint32_t koff = k * TC_UMMA_K * 2;
+            const uint64_t da_hi = umma_desc_sw128(a_hi + koff), da_lo = umma_desc_sw128(a_lo + koff);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(h * 192);
+              const uint64_t dw_hi = umma_desc_sw128(w_hi + h * 96 * 128 + koff);
+              umma_f16_2sm(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (NPASS > 1) {
+                const uint64_t dw_lo = umma_desc_sw128(w_lo + h * 96 * 128 + koff);
+                umma_f16_2sm(d_tmem, da_hi, dw_lo, idesc, 1u);
+                umma_f16_2sm(d_tmem, da_lo, dw_hi, idesc, 1u);
+              }
+            }
+          }
+          umma_commit_2sm_mc(&empty[stage], 3);
+          if (kb == k_blocks - 1) umma_commit_2sm_mc(acc_full, 3);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9): bias + residual + LayerNorm + hi/lo split =====================
+    const int quad = warp & 3, chalf = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = N / 2;             // 192 (NH = 2) or 96 (NH = 1)
+    constexpr int NCH = COLS_PER_WARP / 32;
+    constexpr int EP = Cfg::EPI_PITCH;
+    const int col_lo = chalf * COLS_PER_WARP;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 32 * EP;
+    float* stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::EPI_BYTES);
+    const int lr = lane >> 3, lc = (lane & 7) * 4;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++tcount) {
+      const int m0 = (tile * 2 + crank) * TC_BM;
+      if (!mbar_wait(acc_full, acc_phase)) { if (lane == 0) atomicExch(err_flag, 204); break; }
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+      float s1[8], s2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+      uint32_t v[32];
+      tmem_ld32_issue(t_row + (uint32_t)col_lo, v);
+      // ---- phase A ----
+#pragma unroll 1
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c0 = col_lo + ci * 32;
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * EP + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (ci + 1 < NCH) {
+          tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), v);
+        } else {
+          tc_fence_before();  // every TMEM read of this accumulator has completed
+          if (leader) mbar_arrive(acc_empty); else mbar_arrive_remote(acc_empty, 0);
+        }
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + lc);
+        float4 rs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rs[i] = __ldcs(reinterpret_cast<const float4*>(resid + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + lr;
+          const float4 a = *reinterpret_cast<const float4*>(stg + r * EP + lc);
+          const float o0 = fmaf(a.x, out_scale, b4.x) + rs[i].x, o1 = fmaf(a.y, out_scale, b4.y) + rs[i].y;
+          const float o2 = fmaf(a.z, out_scale, b4.z) + rs[i].z, o3 = fmaf(a.w, out_scale, b4.w) + rs[i].w;
+          s1[i] += (o0 + o1) + (o2 + o3);
+          s2[i] = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, s2[i]))));
+          *reinterpret_cast<float4*>(scratch + (size_t)(m0 + quad * 32 + r) * N + c0 + lc) = make_float4(o0, o1, o2, o3);
+        }
+        __syncwarp();
+      }
+      // ---- row statistics: 8 lanes share a row inside the warp, two warps share it inside the CTA ----
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+        }
+      }
+      float* st = stats + (tcount & 1) * (TC_EPI_WARPS * 32 * 2);
+      if ((lane & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float2*>(st + ((warp - 2) * 32 + 4 * i + lr) * 2) = make_float2(s1[i], s2[i]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+      float mean[8], rstd[8];
+      {
+        const int w0 = quad == 2 ? 0 : (quad == 3 ? 1 : (quad == 0 ? 2 : 3));  // epilogue-warp index of (quad, chalf 0)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + lr;
+          const float2 p0 = *reinterpret_cast<const float2*>(st + (w0 * 32 + r) * 2);
+          const float2 p1 = *reinterpret_cast<const float2*>(st + ((w0 + 4) * 32 + r) * 2);
+          const float m = (p0.x + p1.x) * (1.0f / N);
+          const float var = fmaxf((p0.y + p1.y) * (1.0f / N) - m * m, 0.0f);
+          mean[i] = m;
+          rstd[i] = 1.0f / sqrtf(var + ln_eps);
+        }
+      }
+      // ---- phase B (overlaps the next tile's MMAs) ----
+#pragma unroll 1
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c0 = col_lo + ci * 32;
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + c0 + lc);
+        const float4 e4 = *reinterpret_cast<const float4*>(beta + c0 + lc);
+        float4 xs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xs[i] = *reinterpret_cast<const float4*>(scratch + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const size_t off = (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc;
+          const float o0 = ((xs[i].x - mean[i]) * rstd[i]) * g4.x + e4.x, o1 = ((xs[i].y - mean[i]) * rstd[i]) * g4.y + e4.y;
+          const float o2 = ((xs[i].z - mean[i]) * rstd[i]) * g4.z + e4.z, o3 = ((xs[i].w - mean[i]) * rstd[i]) * g4.w + e4.w;
+          __stcs(reinterpret_cast<float4*>(out + off), make_float4(o0, o1, o2, o3));
+          const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
+          uint2 ph;
+          ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(o_hi + off) = ph;
+          if (NPASS > 1) {
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(o0 - f01.x, o1 - f01.y), l23 = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
+            uint2 pl;
+            pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(o_lo + off) = pl;
+          }
+        }
+      }
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -675,8 +940,11 @@ int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const f
   __half* c_lo = (c_tc && NPASS > 1) ? c_tc->lo : nullptr;
   const CUtensorMap& wh = CL > 1 ? w->half_hi : w->map_hi;
   const CUtensorMap& wl = CL > 1 ? w->half_lo : w->map_lo;
+  // the A row block is streamed: evict-first keeps it from displacing the output in L2 - but only when few
+  // column tiles re-read it (measured: hurts the 6-tile QKV projection, helps the 2-tile ones)
+  const unsigned long long a_policy = (N / BN <= 2) ? TC_EVICT_FIRST : 0x1000000000000000ull;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, wh, wl, bias, resid, C, c_hi, c_lo, M, N, K,
-                                     w->inv_scale, err);
+                                     w->inv_scale, err, a_policy);
   return e == cudaSuccess ? 0 : 12;
 }
 
@@ -718,6 +986,63 @@ inline int tc_gemm(int mode, int epi, const TcPlane* a, const TcWeight* w, const
                    : tc_dispatch_epi<64, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
   }
   return 21;
+}
+
+
+// out = LN(a W^T + bias + resid) * gamma + beta as fp32 + hi/lo planes; N = w->n in {192, 384}; needs M % 256 == 0.
+// mode: 1 = FD_GEMM_TC_3X, 2 = FD_GEMM_TC_1X.  Returns 0 on success.
+template <int NH, int NPASS>
+int tc_gemm_ln_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, const float* gamma,
+                      const float* beta, float eps, float* scratch, float* out, TcPlane* o_tc, int M, int K,
+                      int sm_count, cudaStream_t st) {
+  using Cfg = TcLnCfg<NH, NPASS>;
+  static bool configured = false;
+  auto kern = tc_gemm_ln_kernel<NH, NPASS>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
+    configured = true;
+  }
+  int* err = tc_err_flag();
+  if (!err) return 11;
+  const int tiles = M / (2 * TC_BM);
+  int clusters = sm_count / 2;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, w->half_hi, w->half_lo, bias, resid, gamma, beta,
+                                     eps, scratch, out, o_tc->hi, NPASS > 1 ? o_tc->lo : (__half*)nullptr, M, K,
+                                     w->inv_scale, err);
+  return e == cudaSuccess ? 0 : 12;
+}
+
+inline bool tc_gemm_ln_supported(const TcWeight* w, int M) {
+  // Opt-in (FOLDINGDIFF_B200_FUSE_LN=1).  Measured on B200, config 2: the fused kernel is numerically
+  // equivalent but SLOWER than GEMM + standalone LayerNorm (2.67 vs 2.31 ms per reverse step for the two
+  // projections): ~1 MB of residual / scratch / output traffic per tile is latency-exposed behind only 8
+  // epilogue warps per SM, and 175 full-row tiles over 74 CTA pairs quantise to 3 waves, while the
+  // standalone LayerNorm streams at the HBM roofline with thousands of warps in flight.
+  static const bool enabled = [] { const char* e = getenv("FOLDINGDIFF_B200_FUSE_LN"); return e && e[0] == '1'; }();
+  return enabled && tc_mode() == 2 && w->bn == 192 && (w->n == 192 || w->n == 384) && M % (2 * TC_BM) == 0;
+}
+
+inline int tc_gemm_ln(int mode, const TcPlane* a, const TcWeight* w, const float* bias, const float* resid,
+                      const float* gamma, const float* beta, float eps, float* scratch, float* out, TcPlane* o_tc,
+                      int M, int K, int sm_count, cudaStream_t st) {
+  if (!a || !w || !o_tc || a->k != K || w->k != K || K % TC_BK) return 20;
+  const bool three = mode == 1;
+  if (w->n == 384)
+    return three ? tc_gemm_ln_launch<2, 3>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st)
+                 : tc_gemm_ln_launch<2, 1>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st);
+  return three ? tc_gemm_ln_launch<1, 3>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st)
+               : tc_gemm_ln_launch<1, 1>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st);
 }
 
 }  // namespace fd

@@ -90,10 +90,12 @@ layernorm_kernel(const float* __restrict__ in, const float* __restrict__ resid, 
   float v[VPL];
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) v[i] = in[(size_t)warp * H + lane + 32 * i];
+  // `in` (the GEMM's fp32 output) and `resid` are dead after this kernel: streaming loads (evict-first)
+  // keep them from displacing the operand planes written below, which the next GEMM reads right away.
+  for (int i = 0; i < VPL; ++i) v[i] = __ldcs(in + (size_t)warp * H + lane + 32 * i);
   if (resid) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) v[i] += resid[(size_t)warp * H + lane + 32 * i];
+    for (int i = 0; i < VPL; ++i) v[i] += __ldcs(resid + (size_t)warp * H + lane + 32 * i);
   }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) sum += v[i];
@@ -109,7 +111,7 @@ layernorm_kernel(const float* __restrict__ in, const float* __restrict__ resid, 
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
     const float y = ((v[i] - mean) * rstd) * g[c] + bta[c];
-    out[(size_t)warp * H + c] = y;
+    __stcs(out + (size_t)warp * H + c, y);  // next read is two kernels away (the following LayerNorm's residual)
     if (o_hi) {
       const __half hh = __float2half_rn(y);
       o_hi[(size_t)warp * H + c] = hh;

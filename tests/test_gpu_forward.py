@@ -84,3 +84,28 @@ def test_to_device_roundtrip_and_state_dict(mini_dir):
         model.token_decoder.dense2.bias.add_(1.0)  # parameter edits are picked up (engine rebuild)
     e2 = model(x, torch.zeros(1, dtype=torch.long, device="cuda"), attention_mask=torch.ones(1, 8, device="cuda"))
     assert torch.allclose(e2, e1 + 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("env", [{"FOLDINGDIFF_B200_TC_MODE": "mcast"}, {"FOLDINGDIFF_B200_TC_MODE": "single"},
+                                 {"FOLDINGDIFF_B200_FUSE_LN": "1"}])
+def test_alternative_tensor_core_paths(env, tmp_path):
+    """The A/B variants of the tensor-core path (multicast clusters, single CTA, fused GEMM+LayerNorm) are
+    selected by environment at library load, so each runs in its own process: same forward parity gate."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import load_golden\n"
+        "from gpu_util import FWD_TOL, prefix_mask, prod_model\n"
+        "g = load_golden('prod_forward.npz')\n"
+        "x, t, lengths = torch.from_numpy(g['x']), torch.from_numpy(g['t']), g['lengths'].tolist()\n"
+        "eps = prod_model('tc3x')(x.cuda(), t.cuda(), attention_mask=prefix_mask(lengths, 128).cuda()).cpu()\n"
+        "err = float((eps - torch.from_numpy(g['eps_f32'])).abs().max())\n"
+        "from foldingdiff_b200 import _native\n"
+        "print('err', err, 'tc_status', _native.lib().fd_debug_tc_status())\n"
+        "assert err < FWD_TOL['tc3x'] and _native.lib().fd_debug_tc_status() == 0\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
