@@ -442,7 +442,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float o0 = fmaf(a.x, out_scale, b4.x), o1 = fmaf(a.y, out_scale, b4.y);
           float o2 = fmaf(a.z, out_scale, b4.z), o3 = fmaf(a.w, out_scale, b4.w);
           if (EPI == EPI_BIAS_RESID) { o0 += rs[i].x; o1 += rs[i].y; o2 += rs[i].z; o3 += rs[i].w; }
-          if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3); }
+          if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf_fast(o0); o1 = gelu_erf_fast(o1); o2 = gelu_erf_fast(o2); o3 = gelu_erf_fast(o3); }
           if (C) *reinterpret_cast<float4*>(C + off) = make_float4(o0, o1, o2, o3);
           if (c_hi) {
             const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);

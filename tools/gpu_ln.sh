@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -q -s -k "tc3x" > gpurun_out/test_tc3x
 grep -E "^\[|\]|passed|failed|rror" gpurun_out/test_tc3x.log | tail -14
 python -c "
 from foldingdiff_b200 import _native; import torch; torch.zeros(1).cuda(); print('tc status', _native.lib().fd_debug_tc_status())"
-for f in 1 0; do
+for f in 0; do
 FOLDINGDIFF_B200_FUSE_LN=$f timeout 600 python bench.py --gemm tc3x --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_f$f.json 2> gpurun_out/bench_f$f.err; echo "bench fuse=$f rc=$?"
 python - <<PY
 import json
