@@ -40,6 +40,14 @@ from foldingdiff_b200 import beta_schedules, datasets, synthetic  # noqa: E402
 
 SEED = 7344
 PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
+# From the committed `ncu --set full` capture of this configuration (profiles/r01_gemm_ncu.md, config 2,
+# FD_GEMM_TC_3X, CTA-pair mode): dram__bytes_read.sum + dram__bytes_write.sum per launch, and
+# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active.  Static annotations, not re-measured here.
+NCU_GEMM = {
+    "dram_bytes_per_launch": {"gemm_qkv": 224.9e6, "gemm_attn_out": 80.8e6, "gemm_ffn1": 154.9e6, "gemm_ffn2": 150.8e6},
+    "tensor_pipe_active_pct": {"gemm_qkv": 76.9, "gemm_attn_out": 65.9, "gemm_ffn1": 49.3, "gemm_ffn2": 79.2},
+    "source": "profiles/r01_gemm_ncu.md (FFN1 captured before the fast-GELU epilogue)",
+}
 FALLBACK_PEAK_TFLOPS = 1590.0  # /opt/skills/guides/B200_PROFILING.md fallback (burst)
 
 
@@ -341,7 +349,11 @@ def main():
         dominant = "projection GEMMs (tc_gemm_kernel / sgemm_tn_kernel)" if gemm_ms >= att_ms else "attention_simt_kernel"
         dom_tf = gemm_tf if gemm_ms >= att_ms else att_tf
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": dom_tf / peak_tf, "peak_source": peak_src, "traffic": None,
+                    "frac": dom_tf / peak_tf, "peak_source": peak_src,
+                    "traffic": (float(np.mean(list(NCU_GEMM["dram_bytes_per_launch"].values())))
+                                if (args.workload == "config2" and args.gemm == "tc3x" and gemm_ms >= att_ms) else None),
+                    "traffic_note": "ncu DRAM bytes per GEMM launch, mean over the four projections; " + NCU_GEMM["source"],
+                    "tensor_pipe_active_pct_ncu": NCU_GEMM["tensor_pipe_active_pct"],
                     "gemm_tflops_algorithmic": gemm_tf, "attention_tflops_algorithmic": att_tf,
                     "whole_step_tflops_algorithmic": flops_step * start_t / (ms_per_step * 1e-3) / 1e12,
                     "note": "algorithmic FLOPs (valid tokens, 2 flop/MAC, SURVEY 8d) / CUDA-event kernel time; "

@@ -73,6 +73,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // (same logical chunk, consecutive rows) land in eight different 16-byte bank groups.
 __device__ __forceinline__ int att_sw(int r, int c) { return r * ATT_PITCH + ((c ^ ((r >> 1) & 3)) << 3); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // (x0, x1) -> packed fp16 hi and lo words
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
@@ -106,7 +112,8 @@ __device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const _
     }
   }
   for (int i = gtid; i < nk16; i += ATT_GROUP_WARPS * 32)
-    bias_s[i] = (i < n_keys) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] : 0.0f) : -INFINITY;
+    bias_s[i] = (i < n_keys) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] * 1.44269504088896340736f : 0.0f)
+                             : -INFINITY;  // pre-multiplied by log2(e): the softmax works in log2 units
 }
 
 // Q fragments (A operand of m16n8k16: 16 rows x 32 head dims) of one warp, straight from global.
@@ -217,31 +224,33 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
   }
 
   // ---- scale, bias / mask, softmax (rows g and g + 8 of this warp's block) -----------------------
-  const float inv_sqrt_d = 0.17677669529663688110f;  // 1 / sqrt(32)
+  // logits are kept in log2 units: t = s * (log2e / sqrt(32)) + bias * log2e, p = 2^(t - max t); the bias row
+  // was staged pre-multiplied by log2e (masked keys: -inf).  t - max <= 0, so the bare ex2.approx is safe.
+  const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int nb = 0; nb < 16; ++nb) {
     if (nb < nnb) {
-      const float b0 = Bs[nb * 8 + 2 * t], b1 = Bs[nb * 8 + 2 * t + 1];
-      s[nb][0] = fmaf(s[nb][0], inv_sqrt_d, b0); s[nb][1] = fmaf(s[nb][1], inv_sqrt_d, b1);
-      s[nb][2] = fmaf(s[nb][2], inv_sqrt_d, b0); s[nb][3] = fmaf(s[nb][3], inv_sqrt_d, b1);
+      const float2 b = *reinterpret_cast<const float2*>(Bs + nb * 8 + 2 * t);
+      s[nb][0] = fmaf(s[nb][0], c_scale, b.x); s[nb][1] = fmaf(s[nb][1], c_scale, b.y);
+      s[nb][2] = fmaf(s[nb][2], c_scale, b.x); s[nb][3] = fmaf(s[nb][3], c_scale, b.y);
       m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
       m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
     }
   }
   m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  const float log2e = 1.44269504088896340736f;
-  float sum0 = 0.0f, sum1 = 0.0f;
+  float sum0 = 0.0f, sum1 = 0.0f, sum0b = 0.0f, sum1b = 0.0f;  // two partial sums per row: shorter add chains
 #pragma unroll
   for (int nb = 0; nb < 16; ++nb) {
     if (nb < nnb) {
-      s[nb][0] = exp2f((s[nb][0] - m0) * log2e); s[nb][1] = exp2f((s[nb][1] - m0) * log2e);
-      s[nb][2] = exp2f((s[nb][2] - m1) * log2e); s[nb][3] = exp2f((s[nb][3] - m1) * log2e);
-      sum0 += s[nb][0] + s[nb][1];
-      sum1 += s[nb][2] + s[nb][3];
+      s[nb][0] = ex2_approx(s[nb][0] - m0); s[nb][1] = ex2_approx(s[nb][1] - m0);
+      s[nb][2] = ex2_approx(s[nb][2] - m1); s[nb][3] = ex2_approx(s[nb][3] - m1);
+      sum0 += s[nb][0]; sum0b += s[nb][1];
+      sum1 += s[nb][2]; sum1b += s[nb][3];
     }
   }
+  sum0 += sum0b; sum1 += sum1b;
   sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
 

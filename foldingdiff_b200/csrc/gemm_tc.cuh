@@ -880,13 +880,24 @@ inline void tc_split(const float* src, TcPlane* dst, int rows, int cols, int mod
   tc_split_kernel<<<blocks, 256, 0, st>>>(src, dst->hi, mode == 1 /*FD_GEMM_TC_3X*/ ? dst->lo : nullptr, n4, 1.0f);
 }
 
-inline int* tc_err_flag() {
-  static int* flag = nullptr;
-  if (!flag) {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flag, 0, sizeof(int));
+inline int* tc_err_flag() {  // one flag per device (a process may own several handles on several GPUs)
+  static int* flags[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!flags[dev]) {
+    if (cudaMalloc(&flags[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flags[dev], 0, sizeof(int));
   }
-  return flag;
+  return flags[dev];
+}
+// max-dynamic-smem is a per-device function attribute: remember on which devices it has been set
+inline bool tc_need_configure(unsigned long long* seen_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*seen_mask & bit) return false;
+  *seen_mask |= bit;
+  return true;
 }
 // Reads (and clears) the device-side pipeline error flag; synchronises the device.
 inline int tc_check_error() {
@@ -915,12 +926,10 @@ template <int BN, int NPASS, int EPI, int CL, bool PAIR>
 int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
                  TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN, NPASS, PAIR>;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = tc_gemm_kernel<BN, NPASS, EPI, CL, PAIR>;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
-    configured = true;
-  }
+  if (tc_need_configure(&configured) &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
   int* err = tc_err_flag();
   if (!err) return 11;
   const int tiles = (M / (TC_BM * CL)) * (N / BN);           // cluster-level tiles
@@ -996,12 +1005,10 @@ int tc_gemm_ln_launch(const TcPlane* a, const TcWeight* w, const float* bias, co
                       const float* beta, float eps, float* scratch, float* out, TcPlane* o_tc, int M, int K,
                       int sm_count, cudaStream_t st) {
   using Cfg = TcLnCfg<NH, NPASS>;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = tc_gemm_ln_kernel<NH, NPASS>;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
-    configured = true;
-  }
+  if (tc_need_configure(&configured) &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
   int* err = tc_err_flag();
   if (!err) return 11;
   const int tiles = M / (2 * TC_BM);
