@@ -52,6 +52,8 @@ SIGNATURES = {
     "fd_sample_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32,
                                    C.c_void_p]),
+    "fd_nerf_build": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p]),
     "fd_randn": (C.c_int32, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fd_launch_count": (C.c_int64, [C.c_void_p]),
     "fd_profile_begin": (C.c_int32, [C.c_void_p]),

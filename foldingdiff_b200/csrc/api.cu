@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
+#include "nerf.cuh"
 #include "philox.cuh"
 
 namespace {
@@ -730,6 +731,31 @@ int32_t fd_profile_end(fd_handle* h, float* ms_out, int64_t* launches_out) {
 int32_t fd_profile_num_categories(void) { return CAT_COUNT; }
 
 const char* fd_profile_category_name(int32_t i) { return (i >= 0 && i < CAT_COUNT) ? kCatNames[i] : ""; }
+
+int32_t fd_nerf_build(const float* angles_dev, int32_t batch, int32_t n_pad, int32_t n_features,
+                      const int32_t* lengths, const int32_t* columns, int32_t center, float* coords_out_dev,
+                      void* stream) {
+  if (!angles_dev || !lengths || !columns || !coords_out_dev) return fail(FD_ERR_INVALID, "null argument");
+  if (batch < 1 || n_pad < 1 || n_features < 3) return fail(FD_ERR_INVALID, "bad shape");
+  for (int i = 0; i < 6; ++i)
+    if (columns[i] >= n_features || (i < 3 && columns[i] < 0))
+      return fail(FD_ERR_INVALID, "columns[%d]=%d (phi, psi, omega are required; all must be < n_features)", i, columns[i]);
+  for (int b = 0; b < batch; ++b)
+    if (lengths[b] < 1 || lengths[b] > n_pad) return fail(FD_ERR_INVALID, "lengths[%d]=%d outside [1, %d]", b, lengths[b], n_pad);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* d_len = nullptr;
+  FD_CUDA(cudaMalloc(&d_len, sizeof(int) * batch));
+  if (cudaMemcpyAsync(d_len, lengths, sizeof(int) * batch, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    cudaFree(d_len);
+    return fail(FD_ERR_CUDA, "nerf: H2D lengths");
+  }
+  fd::NerfCols cols{columns[0], columns[1], columns[2], columns[3], columns[4], columns[5]};
+  fd::nerf_kernel<<<(batch + 31) / 32, 32, 0, st>>>(angles_dev, d_len, batch, n_pad, n_features, cols, center, coords_out_dev);
+  int rc = check_launch();
+  cudaStreamSynchronize(st);  // d_len must outlive the kernel
+  cudaFree(d_len);
+  return rc;
+}
 
 int32_t fd_debug_tc_status(void) { return fd::tc_check_error(); }
 

@@ -188,6 +188,23 @@ int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t
                        uint64_t seed, const uint8_t* wrap_mask, int32_t full_history,
                        float* out_host);
 
+/*
+ * Batched NeRF (SURVEY.md section 8f, rank 1 "next" row): internal angles -> backbone coordinates.
+ * Replaces the per-chain Python loop of nerf.NERFBuilder.cartesian_coords / centered_cartesian_coords
+ * (/root/reference/foldingdiff/nerf.py:79-128, place_dihedral :145-204) as called by
+ * angles_and_coords.create_new_chain_nerf (/root/reference/foldingdiff/angles_and_coords.py:112-184).
+ *   angles_dev     : (batch, n_pad, n_features) fp32, the sampler's output layout
+ *   lengths        : HOST int32[batch], residues per chain
+ *   columns        : HOST int32[6] = feature index of {phi, psi, omega, tau (N:CA:C), CA:C:1N, C:1N:1CA};
+ *                    -1 for a bond angle means the reference's default (109 / 115 / 121 degrees)
+ *   center         : 1 = subtract each chain's mean coordinate (the reference's default)
+ *   coords_out_dev : (batch, 3 * n_pad, 3) fp32, atoms in N, CA, C order; rows >= 3 * lengths[b] are 0
+ * Fixed bond lengths 1.34 / 1.46 / 1.54 A and the 1CRN start frame, like the reference. Synchronises.
+ */
+int32_t fd_nerf_build(const float* angles_dev, int32_t batch, int32_t n_pad, int32_t n_features,
+                      const int32_t* lengths, const int32_t* columns, int32_t center, float* coords_out_dev,
+                      void* stream);
+
 /* Fill dst_dev[0..n) with standard normals from the library's Philox4x32-10 stream
  * (seed, offset).  Used by fd_sample_host(noise_host == NULL) and the throughput mode. */
 int32_t fd_randn(float* dst_dev, int64_t n, uint64_t seed, uint64_t offset, void* stream);
