@@ -359,6 +359,34 @@ def main():
                     "note": "algorithmic FLOPs (valid tokens, 2 flop/MAC, SURVEY 8d) / CUDA-event kernel time; "
                             "the 3-pass split issues 3x these MMAs"}
 
+    # ---- section 8f rank-1 row: batched NeRF (angles -> backbone coordinates), reported beside the headline ----
+    nerf_line = None
+    if rank == 0:
+        from foldingdiff_b200 import nerf as fnerf
+        names = ["phi", "psi", "omega", "tau", "CA:C:1N", "C:1N:1CA"]
+        ang = noise_dev.clone()
+        ang[..., 3:] = ang[..., 3:].abs() * 0.2 + 1.7
+        for _ in range(3):
+            fnerf.build_backbone(ang, lengths, names)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            xyz = fnerf.build_backbone(ang, lengths, names)
+        e1.record()
+        torch.cuda.synchronize()
+        gpu_rate = reps * B / (e0.elapsed_time(e1) / 1000.0)
+        nerf_line = {"gpu_structures_per_s": gpu_rate, "atoms_per_structure": "3 x length (N, CA, C)",
+                     "api": "foldingdiff_b200.nerf.build_backbone (fd_nerf_build)", "chains": B}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import nerf as onerf  # CPU baseline leg: the reference's per-chain Python loop, restated
+            host = ang[:8].cpu().numpy()
+            t0 = time.perf_counter()
+            for i in range(8):
+                onerf.build_chain(host[i, : lengths[i]], names)
+            nerf_line["cpu_structures_per_s_1core"] = 8 / (time.perf_counter() - t0)
+            nerf_line["cpu_sample"] = "8 chains, oracle restatement of nerf.NERFBuilder (single core, as one pool worker)"
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, args.cpu_steps, start_t, wrap_all)
@@ -376,7 +404,7 @@ def main():
                        "l2": "inputs larger than L2: ~1 GB of activations per reverse step, 1000 steps per pass",
                        "algorithmic_tflop_per_pass": flops_step * start_t / 1e12},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "next_rows": {"nerf": nerf_line},
         }
         print(json.dumps(line))
     if world > 1:

@@ -69,7 +69,8 @@ def test_cuda_nerf_full_batch_properties():
     for i in (0, 77, 511):
         n = 3 * lengths[i]
         d = (xyz[i, 1:n] - xyz[i, : n - 1]).norm(dim=1)
-        assert torch.allclose(d[0::3], torch.tensor(1.46), atol=2e-4) and torch.allclose(d[1::3], torch.tensor(1.54), atol=2e-4)
+        # the first residue is the (non-ideal) 1CRN start frame; every placed bond has its ideal length
+        assert torch.allclose(d[3::3], torch.tensor(1.46), atol=2e-4) and torch.allclose(d[4::3], torch.tensor(1.54), atol=2e-4)
         assert torch.allclose(d[2::3], torch.tensor(1.34), atol=2e-4)
         assert float(xyz[i, :n].mean(dim=0).abs().max()) < 1e-4
     assert bool(torch.isfinite(xyz).all())
