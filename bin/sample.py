@@ -87,6 +87,14 @@ def main() -> None:
             os.makedirs(d, exist_ok=True)
             for t, snap in enumerate(series):
                 pd.DataFrame(snap, columns=cols).to_csv(d / f"generated_{i}_timestep_{t}.csv.gz")
+    # backbone coordinates on the GPU (fd_nerf_build): one npz with an (3 * length, 3) N/CA/C array per chain
+    from foldingdiff_b200 import nerf as fnerf
+    n_max = max(len(df) for df in dfs)
+    packed = torch.zeros((len(dfs), n_max, len(cols)), dtype=torch.float32)
+    for i, df in enumerate(dfs):
+        packed[i, : len(df)] = torch.from_numpy(df.to_numpy(dtype=np.float32))
+    xyz = fnerf.build_backbone(packed.to(args.device), [len(df) for df in dfs], cols, center=True).cpu().numpy()
+    np.savez_compressed(outdir / "sampled_coords.npz", **{f"generated_{i}": xyz[i, : 3 * len(df)] for i, df in enumerate(dfs)})
     try:  # unchanged post-processing of the reference (NeRF + PDB), if that package is installed
         from foldingdiff.angles_and_coords import create_new_chain_nerf  # type: ignore
         os.makedirs(outdir / "sampled_pdb", exist_ok=True)

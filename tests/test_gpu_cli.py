@@ -1,0 +1,37 @@
+"""bin/sample.py end to end on the mini fixture (with a mean-offset file): flags and output tree of the reference CLI."""
+import gzip
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import ROOT, mini_state_dict, write_model_dir
+from foldingdiff_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sample_cli(tmp_path):
+    sd, cfg, targs, ckpt = mini_state_dict()
+    targs = dict(targs, timesteps=20, variance_schedule="linear")
+    mdir = write_model_dir(str(tmp_path / "model"), sd, cfg, targs, ckpt, mean_offset=synthetic.CATH_MEAN_OFFSET)
+    out = tmp_path / "out"
+    cmd = [sys.executable, os.path.join(ROOT, "bin", "sample.py"), "-m", mdir, "-o", str(out), "-n", "2", "-l", "50", "53",
+           "-b", "4", "--seed", "11", "--fullhistory"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    files = sorted(os.listdir(out / "sampled_angles"))
+    assert [f for f in files if f.endswith(".csv.gz")] == [f"generated_{i}.csv.gz" for i in range(6)]
+    df = pd.read_csv(out / "sampled_angles" / "generated_5.csv.gz", index_col=0)
+    assert df.shape == (52, 6) and list(df.columns) == ["phi", "psi", "omega", "tau", "CA:C:1N", "C:1N:1CA"]
+    assert np.abs(df.to_numpy()).max() <= np.pi + 1e-6
+    assert len(os.listdir(out / "sampled_angles" / "sample_history" / "generated_0")) == 20
+    assert sorted(os.listdir(out / "model_snapshot")) == ["config.json", "models", "training_args.json"]
+    xyz = np.load(out / "sampled_coords.npz")
+    assert xyz["generated_0"].shape == (150, 3) and np.isfinite(xyz["generated_5"]).all()
+    # a non-empty output directory is refused, like the reference (bin/sample.py:299)
+    again = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert again.returncode != 0 and "to be empty" in again.stderr
