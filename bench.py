@@ -213,18 +213,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        rate, cores, sample, dt = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, max(1, args.cpu_steps), start_t, wrap_all)
-        # each bench "step" of this arm is the bounded sample; W warm-ups + K timed repeats of it
-        reps = []
+        # each bench "step" of this arm is one bounded sample (cpu_steps reverse steps over cpu_chains chains of the
+        # workload's length mix, extrapolated to the full loop); W warm-up samples, then K timed ones
+        reps, dts = [], []
+        sample, cores = "", os.cpu_count() or 1
         for i in range(args.warmup + args.steps):
-            r, _, _, d = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, 1, start_t, wrap_all)
+            r, cores, sample, d = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, max(1, args.cpu_steps), start_t, wrap_all)
             if i >= args.warmup:
                 reps.append(r)
-        value = float(np.mean(reps)) if reps else rate
+                dts.append(d)
+        value = float(np.mean(reps))
+        dt = float(np.mean(dts))
         line = {
             "impl": "reference", "metric": "backbones/sec", "value": value, "unit": "backbones/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * args.cpu_chains / value, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1000.0 * dt * max(1, args.cpu_steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "timesteps": T, "note": "CPU path: fp32 torch restatement of the reference forward "
                        "(HF 4.11.3 encoder not installable) + the reference's loop arithmetic"},
