@@ -58,22 +58,46 @@ def build_parser() -> argparse.ArgumentParser:
 
 def main() -> None:
     args = build_parser().parse_args()
-    os.makedirs(args.outdir, exist_ok=True)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = 0
+    if world > 1:
+        # launched with torchrun: one process per GPU, chains sharded round-robin over the ranks, one all-gather
+        # of the finished angles per batch, rank 0 writes the outputs (foldingdiff_b200/distributed.py)
+        import torch.distributed as dist
+        assert not args.fullhistory, "--fullhistory is single-GPU only"
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        args.device = f"cuda:{local}"
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(args.device))
+        rank = dist.get_rank()
     outdir = Path(args.outdir)
-    assert not os.listdir(outdir), f"Expected {outdir} to be empty!"
     if not os.path.isdir(args.model):
         raise SystemExit(f"{args.model} is not a directory; hub ids need network access, which this build does not assume")
     if args.testcomparison:
         raise SystemExit("--testcomparison needs the reference's CATH dataset pipeline (out of scope here)")
-    os.makedirs(outdir / "plots", exist_ok=True)
+    if rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+        assert not os.listdir(outdir), f"Expected {outdir} to be empty!"
+        os.makedirs(outdir / "plots", exist_ok=True)
     train_dset = build_datasets(Path(args.model))
-    model = modelling.BertForDiffusionBase.from_dir(args.model, copy_to=outdir / "model_snapshot").to(torch.device(args.device))
+    model = modelling.BertForDiffusionBase.from_dir(
+        args.model, copy_to=outdir / "model_snapshot" if rank == 0 else None).to(torch.device(args.device))
     lo, hi = args.lengths
     assert lo < hi and hi <= train_dset.dset.pad
 
-    torch.manual_seed(args.seed)
-    sampled = sampling.sample(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
-                              history="full" if args.fullhistory else "final")
+    if world > 1:
+        from foldingdiff_b200 import distributed as fdist
+        finals = fdist.sample_sharded(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
+                                      seed=args.seed)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+        sampled = [f[None] for f in finals]
+    else:
+        torch.manual_seed(args.seed)
+        sampled = sampling.sample(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
+                                  history="full" if args.fullhistory else "final")
     cols = train_dset.feature_names["angles"]
     dfs = [pd.DataFrame(s[-1], columns=cols) for s in sampled]
     angles_dir = outdir / "sampled_angles"

@@ -69,3 +69,44 @@ def sample_final_sharded(model, lengths: Sequence[int], noise: torch.Tensor, tim
         return out[-1].to(dev)
 
     return sharded_final_angles(run, lengths, noise, group=group)
+
+
+def sample_sharded(model, train_dset, n: int = 10, sweep_lengths=(50, 128), batch_size: int = 512,
+                   feature_key: str = "angles", seed: Optional[int] = None, group=None):
+    """
+    Multi-GPU counterpart of `sampling.sample(..., history="final")`: every rank builds the same length list and
+    draws the same initial noise (same CPU seed), samples its round-robin share of each batch chunk, and one
+    all-gather per chunk returns the final angles in the reference's order.  Returns, on every rank, the list of
+    `(length, n_features)` arrays with the training mean offset added and angular columns re-wrapped, exactly as
+    `sampling.sample` post-processes them (reference sampling.py:205-222).
+    """
+    import numpy as np
+
+    from . import sampling, utils
+
+    lo, hi = sweep_lengths
+    if not lo < hi:
+        raise ValueError(f"Minimum length {lo} must be less than maximum {hi}")
+    lengths = [l for l in range(lo, hi) for _ in range(n)]
+    rank, _ = _world(group)
+    if seed is not None:
+        torch.manual_seed(seed)  # identical initial noise on every rank (CPU generator)
+        if torch.cuda.is_available():
+            # ... but an independent stream of per-step normals per rank: with the same device seed, chain k of
+            # every rank would be driven by the same z_t sequence
+            torch.cuda.manual_seed(seed + 1000003 * rank)
+    out = []
+    for chunk in utils.seq_to_groups(lengths, batch_size):
+        noise = train_dset.sample_noise(torch.zeros((len(chunk), train_dset.pad, model.n_inputs), dtype=torch.float32))
+        noise = noise[:, : max(chunk), :]
+        final = sample_final_sharded(model, chunk, noise, train_dset.timesteps, train_dset.alpha_beta_terms["betas"],
+                                     train_dset.feature_is_angular[feature_key], group=group)
+        out.extend(final[i, :l].numpy() for i, l in enumerate(chunk))
+    inner = getattr(train_dset, "dset", None)
+    if inner is not None and hasattr(inner, "get_masked_means") and inner.get_masked_means() is not None:
+        means = inner.get_masked_means()
+        out = [s + means for s in out]
+        idx = np.where(train_dset.feature_is_angular[feature_key])[0]
+        for s in out:
+            s[..., idx] = utils.modulo_with_wrapped_range(s[..., idx], -np.pi, np.pi)
+    return out

@@ -232,3 +232,19 @@ def test_full_size_batch_properties(gemm):
         assert float((xs[j, :l] - x[i, :l]).abs().max()) < 1e-4
     # padded rows untouched
     assert torch.equal(x[0, lengths[0]:].cpu(), noise[0, lengths[0]:])
+
+
+@pytest.mark.gpu
+def test_sample_sharded_single_rank_equals_sample(mini_dir):
+    """world = 1: distributed.sample_sharded is sampling.sample(history="final") on the same seed, bit for bit."""
+    from foldingdiff_b200 import distributed as fdist
+    from foldingdiff_b200.datasets import AnglesEmptyDataset, NoisedAnglesDataset
+    model = mini_model(mini_dir, "tc3x")
+    shell = AnglesEmptyDataset("canonical-full-angles", pad=128, mean_offset=np.linspace(-0.5, 0.5, 6))
+    dset = NoisedAnglesDataset(shell, dset_key="angles", timesteps=40, beta_schedule="linear")
+    torch.manual_seed(11)
+    ref = sampling.sample(model, dset, n=2, sweep_lengths=(20, 26), batch_size=5, history="final")
+    got = fdist.sample_sharded(model, dset, n=2, sweep_lengths=(20, 26), batch_size=5, seed=11)
+    assert len(ref) == len(got) == 12
+    for r, g in zip(ref, got):
+        np.testing.assert_array_equal(r[-1], g)
