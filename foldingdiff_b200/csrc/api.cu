@@ -10,6 +10,7 @@
 
 #include "../../include/foldingdiff_b200.h"
 #include "attention_mma.cuh"
+#include "attention_pool.cuh"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
@@ -69,6 +70,7 @@ struct fd_handle {
   // workspace (rows_pad x width), fp32
   float *h = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *a = nullptr, *inter = nullptr;
   fd::TcActs tc;  // hi / lo operand planes of the activations (tensor-core modes)
+  CUtensorMap att_hi, att_lo;  // per-head K / V boxes of the qkv planes (attention_pool.cuh)
   long long launches = 0;
   // optional CUDA-event profiler (fd_profile_begin / fd_profile_end)
   bool prof_on = false;
@@ -180,14 +182,25 @@ void launch_attention(fd_handle* H, const float* dist, cudaStream_t st) {
 }
 
 // tensor-core attention on the fp16 hi / lo planes (tc modes): qkv planes -> ctx planes
-void launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
+int launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
   const int items = H->batch * H->d.heads;
   const int want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS;
   const int grid = want < H->sm_count ? want : H->sm_count;
   const size_t smem = fd::att_smem_bytes();
   const float* bias = H->has_key_bias ? H->key_bias : nullptr;
   ProfScope ps(H, CAT_ATTN, st);
-  if (H->gemm_mode == FD_GEMM_TC_3X)
+  if (fd::attp_enabled()) {
+    int rc;
+    if (H->gemm_mode == FD_GEMM_TC_3X)
+      rc = fd::attp_launch<true>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
+                                 H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
+                                 H->sm_count, st);
+    else
+      rc = fd::attp_launch<false>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
+                                  H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
+                                  H->sm_count, st);
+    if (rc) return fail(FD_ERR_CUDA, "attention launch failed (%d)", rc);
+  } else if (H->gemm_mode == FD_GEMM_TC_3X)
     fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, smem, st>>>(
         H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
         H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
@@ -196,6 +209,7 @@ void launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
         H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
         H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
   H->launches++;
+  return FD_OK;
 }
 
 template <int VPL, bool SAMPLE>
@@ -252,7 +266,7 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
     int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, w.b_qkv, nullptr, tcm ? nullptr : H->qkv,
                      3 * Hd, Hd, &H->tc.h, tcm ? &H->tc.qkv : nullptr, st);
     if (rc) return rc;
-    if (tcm) launch_attention_mma(H, w, st);
+    if (tcm) { rc = launch_attention_mma(H, w, st); if (rc) return rc; }
     else launch_attention(H, w.dist, st);
     const bool fuse = tcm && fd::tc_gemm_ln_supported(&w.to, H->rows_pad);
     if (fuse) {
@@ -478,6 +492,8 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     FD_CUDA(cudaMalloc(&h->a, sizeof(float) * r * Hd));
     FD_CUDA(cudaMalloc(&h->inter, sizeof(float) * r * I));
     if (fd::tc_alloc_acts(&h->tc, rows_pad, Hd, I)) return fail(FD_ERR_CUDA, "tensor-core workspace allocation failed");
+    if (fd::attp_make_map(&h->att_hi, h->tc.qkv.hi, rows_pad, 3 * Hd) || fd::attp_make_map(&h->att_lo, h->tc.qkv.lo, rows_pad, 3 * Hd))
+      return fail(FD_ERR_CUDA, "attention tensor map creation failed");
     h->cap_batch = batch; h->cap_rows = rows_pad; h->cap_bn = batch * n_pad;
     // rows beyond the last valid one are never written by the row-limited kernels: keep them 0
     FD_CUDA(cudaMemsetAsync(h->h, 0, sizeof(float) * r * Hd, st));
@@ -675,9 +691,10 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
     dim3 grid(heads, batch);
     fd::attention_simt_kernel<<<grid, 128, attn_smem_bytes(n_pad, n_pad), st>>>(qkv_dev, d_rs, d_nr, d_nk, nullptr, n_pad, dist_dev, 128, H, ctx_out_dev);
   } else {
-    const size_t nq = (size_t)rows * 3 * H, nc = (size_t)rows * H, ne = (size_t)fd::ATT_E_TABLE * FD_HEAD_DIM;
+    const size_t nq = (size_t)rows * 3 * H, nqa = (size_t)(rows + 128) * 3 * H, nc = (size_t)rows * H, ne = (size_t)fd::ATT_E_TABLE * FD_HEAD_DIM;
     __half *q_hi, *q_lo, *c_hi, *c_lo, *e_hi, *e_lo; float* e_pad;
-    FD_CUDA(cudaMalloc(&q_hi, nq * 2)); FD_CUDA(cudaMalloc(&q_lo, nq * 2)); FD_CUDA(cudaMalloc(&c_hi, nc * 2)); FD_CUDA(cudaMalloc(&c_lo, nc * 2));
+    FD_CUDA(cudaMalloc(&q_hi, nqa * 2)); FD_CUDA(cudaMalloc(&q_lo, nqa * 2));
+    FD_CUDA(cudaMemsetAsync(q_hi, 0, nqa * 2, st)); FD_CUDA(cudaMemsetAsync(q_lo, 0, nqa * 2, st)); FD_CUDA(cudaMalloc(&c_hi, nc * 2)); FD_CUDA(cudaMalloc(&c_lo, nc * 2));
     FD_CUDA(cudaMalloc(&e_hi, ne * 2)); FD_CUDA(cudaMalloc(&e_lo, ne * 2)); FD_CUDA(cudaMalloc(&e_pad, ne * 4));
     FD_CUDA(cudaMemsetAsync(e_pad, 0, ne * 4, st)); FD_CUDA(cudaMemsetAsync(c_hi, 0, nc * 2, st)); FD_CUDA(cudaMemsetAsync(c_lo, 0, nc * 2, st));
     FD_CUDA(cudaMemcpyAsync(e_pad, dist_dev, sizeof(float) * 255 * FD_HEAD_DIM, cudaMemcpyDeviceToDevice, st));
@@ -689,7 +706,14 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int items = batch * heads, want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS, grid = want < sms ? want : sms;
-    if (mode == FD_GEMM_TC_3X)
+    if (fd::attp_enabled()) {
+      CUtensorMap m_hi, m_lo;
+      int arc = fd::attp_make_map(&m_hi, q_hi, rows + 128, 3 * H) || fd::attp_make_map(&m_lo, q_lo, rows + 128, 3 * H);
+      if (!arc) arc = mode == FD_GEMM_TC_3X
+          ? fd::attp_launch<true>(m_hi, m_lo, q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st)
+          : fd::attp_launch<false>(m_hi, m_lo, q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st);
+      if (arc) rc = fail(FD_ERR_CUDA, "debug attention: pool launch failed (%d)", arc);
+    } else if (mode == FD_GEMM_TC_3X)
       fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
     else
       fd::attention_mma_kernel<false><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
