@@ -24,8 +24,9 @@ namespace fd {
 constexpr int ATTP_NB = 4;                           // ring slots
 constexpr int ATTP_SLOT_HALVES = 4 * ATT_KV_HALVES;  // {K hi, K lo, V hi, V lo}, 8 KB each
 
-struct AttpSlot {  // descriptor of the item resident (or arriving) in a ring slot
-  int r0, n_rows, n_keys, head, nb, pad0, pad1, pad2;
+struct AttpSlot {  // descriptor of the item resident (or arriving) in a ring slot; read with one 8-byte LDS
+  int r0;        // first packed row of the chain
+  uint32_t dims; // n_rows | n_keys << 8 | row blocks << 16 | head << 24
 };
 struct AttpCtl {
   unsigned long long full[ATTP_NB];  // mbarriers: TMA bytes of the slot have landed
@@ -44,7 +45,21 @@ constexpr size_t attp_smem_bytes() {
          + sizeof(AttpCtl) + 1024;                   // control block + slack for the 1024-byte alignment
 }
 
-__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+// Shared-state reads go through explicit ld.volatile.shared (LDS): a volatile load through a generic pointer
+// compiles to LD.E.STRONG.SYS, which ncu showed as the hottest stall of the first version of this kernel.
+__device__ __forceinline__ uint32_t lds_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(void* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 
 // Bring item number `s` of this CTA's list into ring slot s % ATTP_NB.  Called by ONE whole warp.
 template <bool THREE>
@@ -61,8 +76,8 @@ __device__ __forceinline__ void attp_issue(AttpCtl* ctl, __half* ring, float* bi
   for (int i = lane; i < 128; i += 32)  // log2 units, like the logits; keys >= n_keys are masked
     Bs[i] = (i < nk) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] * 1.44269504088896340736f : 0.0f) : -INFINITY;
   if (lane == 0) {
-    AttpSlot& d = ctl->slot[b];
-    d.r0 = r0; d.n_rows = nr; d.n_keys = nk; d.head = head; d.nb = (nr + 15) >> 4;
+    ctl->slot[b].r0 = r0;
+    ctl->slot[b].dims = (uint32_t)nr | (uint32_t)nk << 8 | (uint32_t)((nr + 15) >> 4) << 16 | (uint32_t)head << 24;
     ctl->done[b] = 0;
   }
   __syncwarp();
@@ -79,7 +94,7 @@ __device__ __forceinline__ void attp_issue(AttpCtl* ctl, __half* ring, float* bi
       tma_load_2d(dst + 3 * ATT_KV_HALVES, map_lo, bar, 2 * H + head * FD_HEAD_DIM, r0);
     }
     __threadfence_block();
-    *reinterpret_cast<volatile int*>(&ctl->seq[b]) = s;  // publish: descriptor, bias row and barrier phase are set
+    sts_u32(&ctl->seq[b], (uint32_t)s);  // publish: descriptor, bias row and barrier phase are set
   }
   __syncwarp();
 }
@@ -130,19 +145,18 @@ attention_pool_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
     // ---- take the next row block of the oldest item that still has one -------------------------------
     int s = -1, rb = 0;
     if (lane == 0) {
-      const long long t0 = clock64();
+      int spins = 0;
       for (;;) {
-        const unsigned int st = *reinterpret_cast<volatile unsigned int*>(&ctl->ticket);
+        const uint32_t st = lds_u32(&ctl->ticket);
         const int ts = (int)(st >> 8), trb = (int)(st & 255u);
         if (ts >= n_slots) break;  // nothing left for this CTA
-        if (ld_volatile(&ctl->seq[ts % ATTP_NB]) != ts) {  // its slot is still being drained by the item before
-          if (clock64() - t0 > 4000000000LL) { atomicExch(err_flag, 3); s = -2; break; }
+        if ((int)lds_u32(&ctl->seq[ts % ATTP_NB]) != ts) {  // its slot is still being drained by the item before
+          if (++spins > (1 << 24)) { atomicExch(err_flag, 3); s = -2; break; }  // bounded: never hang the GPU
           __nanosleep(64);
           continue;
         }
-        __threadfence_block();
-        const int nb = ld_volatile(&ctl->slot[ts % ATTP_NB].nb);
-        const unsigned int nxt = (trb + 1 < nb) ? st + 1u : (unsigned int)(ts + 1) << 8;
+        const int nb = (int)((lds_u32(&ctl->slot[ts % ATTP_NB].dims) >> 16) & 255u);
+        const uint32_t nxt = (trb + 1 < nb) ? st + 1u : (uint32_t)(ts + 1) << 8;
         if (atomicCAS(&ctl->ticket, st, nxt) == st) { s = ts; rb = trb; break; }
       }
     }
@@ -150,10 +164,9 @@ attention_pool_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
     rb = __shfl_sync(0xffffffffu, rb, 0);
     if (s < 0) break;
     const int b = s % ATTP_NB;
-    __threadfence_block();
-    const int r0 = ld_volatile(&ctl->slot[b].r0), n_rows = ld_volatile(&ctl->slot[b].n_rows);
-    const int n_keys = ld_volatile(&ctl->slot[b].n_keys), head = ld_volatile(&ctl->slot[b].head);
-    const int nb = ld_volatile(&ctl->slot[b].nb);
+    const uint2 d = lds_u64(&ctl->slot[b]);
+    const int r0 = (int)d.x, n_rows = (int)(d.y & 255u), n_keys = (int)((d.y >> 8) & 255u);
+    const int nb = (int)((d.y >> 16) & 255u), head = (int)(d.y >> 24);
     const int l0 = rb * 16;
     uint32_t qa_hi[2][4], qa_lo[2][4];
     att_load_q<THREE>(qa_hi, qa_lo, qkv_hi, qkv_lo, r0, l0, n_rows, head, H);
@@ -161,6 +174,7 @@ attention_pool_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
       if (lane == 0) atomicExch(err_flag, 4);
       break;
     }
+    __threadfence_block();  // the issuer's bias row (generic stores) is ordered before its seq publication
     att_rows<THREE>(ring + (size_t)b * ATTP_SLOT_HALVES, Es_hi, Es_lo, Rw, bias_rows + b * 128, qa_hi, qa_lo, r0, l0,
                     n_rows, n_keys, head, H, ctx_hi, ctx_lo);
     // ---- the warp that finishes an item's last block refills the slot --------------------------------
