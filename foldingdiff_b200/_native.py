@@ -65,6 +65,7 @@ SIGNATURES = {
     "fd_debug_attention": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fd_debug_tc_status": (C.c_int32, []),
+    "fd_debug_attention_dump": (C.c_int32, [C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -11,6 +11,7 @@
 #include "../../include/foldingdiff_b200.h"
 #include "attention_mma.cuh"
 #include "attention_pool.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
@@ -189,7 +190,11 @@ int launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
   const size_t smem = fd::att_smem_bytes();
   const float* bias = H->has_key_bias ? H->key_bias : nullptr;
   ProfScope ps(H, CAT_ATTN, st);
-  if (fd::attp_enabled()) {
+  if (fd::atc_enabled() && H->gemm_mode == FD_GEMM_TC_3X) {
+    const int rc = fd::atc_launch(H->att_hi, H->att_lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
+                                  H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo, H->sm_count, st);
+    if (rc) return fail(FD_ERR_CUDA, "attention launch failed (%d)", rc);
+  } else if (fd::attp_enabled()) {
     int rc;
     if (H->gemm_mode == FD_GEMM_TC_3X)
       rc = fd::attp_launch<true>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
@@ -706,7 +711,12 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int items = batch * heads, want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS, grid = want < sms ? want : sms;
-    if (fd::attp_enabled()) {
+    if (fd::atc_enabled() && mode == FD_GEMM_TC_3X) {
+      CUtensorMap m_hi, m_lo;
+      int arc = fd::attp_make_map(&m_hi, q_hi, rows + 128, 3 * H) || fd::attp_make_map(&m_lo, q_lo, rows + 128, 3 * H);
+      if (!arc) arc = fd::atc_launch(m_hi, m_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st);
+      if (arc) rc = fail(FD_ERR_CUDA, "debug attention: tcgen05 launch failed (%d)", arc);
+    } else if (fd::attp_enabled()) {
       CUtensorMap m_hi, m_lo;
       int arc = fd::attp_make_map(&m_hi, q_hi, rows + 128, 3 * H) || fd::attp_make_map(&m_lo, q_lo, rows + 128, 3 * H);
       if (!arc) arc = mode == FD_GEMM_TC_3X
@@ -782,5 +792,10 @@ int32_t fd_nerf_build(const float* angles_dev, int32_t batch, int32_t n_pad, int
 }
 
 int32_t fd_debug_tc_status(void) { return fd::tc_check_error(); }
+
+int32_t fd_debug_attention_dump(float* dump_dev) {
+  fd::atc_debug_dump() = dump_dev;
+  return FD_OK;
+}
 
 }  // extern "C"

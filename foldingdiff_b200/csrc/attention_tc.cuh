@@ -1,0 +1,420 @@
+// Relative-key attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   S[l, r] = (q_l . k_r + q_l . E[l - r + 127]) / sqrt(32) + bias_r ;  ctx_l = softmax_r(S) V
+//   (transformers 4.11.3 BertSelfAttention, position_embedding_type = "relative_key";
+//    call site /root/reference/foldingdiff/modelling.py:473)
+//
+// Work item = one (chain, head): the whole chain is ONE 128-row MMA tile (n <= 128 residues).  Per item
+//
+//   S = Q K^T          tcgen05.mma  M = 128, N = nk32, K = 32      (nk32 = keys rounded up to 32)
+//   R = Q Ewin^T       tcgen05.mma  M = 128, N = nk32 + nr32       Ewin = rows [128 - nk32, 128 + nr32) of the
+//                                                                   layer's distance table (resident in smem)
+//   S[l, r] += R[l, l - r + nk32 - 1]      the Toeplitz gather ("skew"): thread l owns TMEM lane l, so it only
+//                                          ever needs ITS OWN row of R at a lane-dependent column shift; the
+//                                          shift goes through a thread-private shared-memory row (64-column
+//                                          window per 32 keys: STS.128 in, 32 scalar LDS out, conflict-free)
+//   P = exp2(S' - max) in registers (one thread = one query row), written back to TMEM as fp16 hi / lo
+//   O = P V            tcgen05.mma  M = 128, N = 32, A = P from TMEM, B = V straight from the TMA tile
+//                      (MN-major descriptor: V is [key][dim], no transpose pass)
+//
+// every product as the error-compensated triple hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (the
+// scheme of gemm_tc.cuh).  Q / K / V tiles (fp16 hi / lo planes written by the QKV GEMM epilogue) arrive by
+// TMA, 64-byte swizzle, into a 3-slot ring.
+//
+// Warp roles (384 threads, one persistent CTA per SM):  warps 0..3 and 4..7 = two softmax warpgroups that take
+// alternate items, warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner (warps 10, 11 only pad the producer
+// warpgroup so that setmaxnreg can move its registers to the softmax threads).  TMEM (512 columns):
+// S [0,128) | R [128,384) | P hi [384,416) lo [416,448) (64 keys per round) | O [448,480).  S and R are single
+// buffered: a warpgroup releases them as soon as its rows sit in registers (sr_empty), so the S/R MMAs of
+// item i+1 run under the softmax of item i, and P V of item i runs under the S/R load of item i+1.
+//
+// Every mbarrier wait is bounded (mbar_wait): a broken pipeline sets the error flag and ends the kernel.
+#pragma once
+#include "attention_pool.cuh"
+
+namespace fd {
+
+constexpr int ATC_SLOTS = 3;
+constexpr int ATC_PLANE_BYTES = 128 * 64;            // 128 rows x 32 halves, 64-byte rows
+constexpr int ATC_SLOT_BYTES = 6 * ATC_PLANE_BYTES;  // Q hi, Q lo, K hi, K lo, V hi, V lo
+constexpr int ATC_SCR_PITCH = 68;                    // words per thread-private skew row (== 4 mod 32)
+constexpr int ATC_THREADS = 384;  // warpgroups: 0 and 1 = softmax, 2 = producers (warp 8 TMA, warp 9 MMA)
+constexpr uint32_t ATC_COL_S = 0, ATC_COL_R = 128, ATC_COL_P = 384, ATC_COL_O = 448;
+constexpr int ATC_DBG_ROW = 128 + 128 + 32 + 2;      // floats per row of the debug dump
+
+constexpr size_t atc_smem_bytes() {
+  return (size_t)ATC_SLOTS * ATC_SLOT_BYTES + 2 * ATT_E_TABLE * 64   // ring + E hi / lo
+         + (size_t)128 * ATC_SCR_PITCH * 4                           // skew scratch (one warpgroup at a time)
+         + 256 + 1024;                                               // barriers + alignment slack
+}
+
+// Operand descriptors, high 32 bits (SBO | version 1 | layout type) - host-computed so a debug run can override
+// them from the environment; the low word is (address >> 4) | LBO << 16.
+struct AtcDesc {
+  uint32_t k_hi32;    // K-major, 64-byte swizzle: 8-row groups 512 bytes apart
+  uint32_t v_hi32;    // MN-major, 64-byte swizzle: 8-key groups 512 bytes apart
+  uint32_t k_lbo, v_lbo;
+  uint32_t pv_idesc;  // kind::f16 instruction descriptor of P V (N = 32, B MN-major)
+};
+inline AtcDesc atc_default_desc() {
+  AtcDesc d;
+  d.k_hi32 = (512u >> 4) | (1u << 14) | (4u << 29);
+  d.v_hi32 = (512u >> 4) | (1u << 14) | (4u << 29);
+  d.k_lbo = 1; d.v_lbo = 1;
+  d.pv_idesc = umma_idesc_f16(32) | (1u << 16);
+  auto env = [](const char* name, uint32_t& v) {
+    const char* e = getenv(name);
+    if (e && e[0]) v = (uint32_t)strtoul(e, nullptr, 0);
+  };
+  env("FOLDINGDIFF_B200_ATC_KHI", d.k_hi32); env("FOLDINGDIFF_B200_ATC_VHI", d.v_hi32);
+  env("FOLDINGDIFF_B200_ATC_KLBO", d.k_lbo); env("FOLDINGDIFF_B200_ATC_VLBO", d.v_lbo);
+  env("FOLDINGDIFF_B200_ATC_PVIDESC", d.pv_idesc);
+  return d;
+}
+
+__device__ __forceinline__ uint64_t atc_desc(uint32_t smem_addr, uint32_t lbo, uint32_t hi32) {
+  return (uint64_t)(((smem_addr & 0x3FFFFu) >> 4) | (lbo << 16)) | ((uint64_t)hi32 << 32);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct AtcItem {
+  int chain, head, r0, n_rows, n_keys, nk32, nr32;
+};
+__device__ __forceinline__ AtcItem atc_item(int it, int n_items, int heads, const int* __restrict__ row_start,
+                                            const int* __restrict__ n_rows_arr, const int* __restrict__ n_keys_arr) {
+  AtcItem a;
+  const int item = n_items - 1 - ((int)blockIdx.x + it * (int)gridDim.x);  // batches are length-sorted: long first
+  a.chain = item / heads; a.head = item % heads;
+  a.r0 = row_start[a.chain]; a.n_rows = n_rows_arr[a.chain]; a.n_keys = n_keys_arr[a.chain];
+  a.nk32 = (a.n_keys + 31) & ~31; a.nr32 = (a.n_rows + 31) & ~31;
+  return a;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const int* __restrict__ row_start, const int* __restrict__ n_rows_arr,
+                    const int* __restrict__ n_keys_arr, const float* __restrict__ key_bias, int n_pad,
+                    const __half* __restrict__ e_hi, const __half* __restrict__ e_lo, int H, int heads, int n_items,
+                    __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo, AtcDesc dsc, float* __restrict__ dbg,
+                    int* __restrict__ err_flag) {
+  extern __shared__ uint8_t atc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  __half* Es_hi = reinterpret_cast<__half*>(smem + ATC_SLOTS * ATC_SLOT_BYTES);
+  __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
+  float* scr = reinterpret_cast<float*>(Es_lo + ATT_E_TABLE * ATT_PITCH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scr + 128 * ATC_SCR_PITCH);
+  uint64_t* kv_full = bars;                  // [3] TMA -> MMA
+  uint64_t* kv_empty = bars + ATC_SLOTS;     // [3] MMA (commit) -> TMA
+  uint64_t* sr_full = bars + 2 * ATC_SLOTS;  // MMA -> softmax
+  uint64_t* sr_empty = sr_full + 1;          // softmax -> MMA
+  uint64_t* p_full = sr_full + 2;            // [2] softmax -> MMA, per 64-key round
+  uint64_t* p_empty = sr_full + 4;           // [2] MMA -> softmax
+  uint64_t* o_full = sr_full + 6;            // MMA -> softmax
+  uint64_t* o_empty = sr_full + 7;           // softmax -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+
+  if (tid == 0) {
+    for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(sr_full, 1); mbar_init(sr_empty, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  // the layer's distance table: 256 rows x 64 bytes per plane, 64-byte swizzle (same layout the TMA tiles have)
+  for (int i = tid; i < ATT_E_TABLE * 4; i += ATC_THREADS) {
+    const int r = i >> 2;
+    cp_async16(Es_hi + att_sw(r, i & 3), e_hi + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
+    cp_async16(Es_lo + att_sw(r, i & 3), e_lo + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
+  }
+  cp_async_wait_all();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above -> tensor-core (async proxy) reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // register reallocation between the warpgroups (pool = 384 x 168): producers keep 40, softmax threads get 232 -
+  // one query row is 128 fp32 logits plus the fp16 hi / lo staging, which does not fit the static 168
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int slot = it % ATC_SLOTS, use = it / ATC_SLOTS;
+        const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+        if (!mbar_wait(&kv_empty[slot], (uint32_t)((use & 1) ^ 1))) { atomicExch(err_flag, 301); break; }
+        uint8_t* s = ring + (size_t)slot * ATC_SLOT_BYTES;
+        const int cq = a.head * FD_HEAD_DIM;
+        mbar_expect_tx(&kv_full[slot], ATC_SLOT_BYTES);
+        tma_load_2d(s, &map_hi, &kv_full[slot], cq, a.r0);
+        tma_load_2d(s + 2 * ATC_PLANE_BYTES, &map_hi, &kv_full[slot], H + cq, a.r0);
+        tma_load_2d(s + 1 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], cq, a.r0);
+        tma_load_2d(s + 3 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], H + cq, a.r0);
+        tma_load_2d(s + 4 * ATC_PLANE_BYTES, &map_hi, &kv_full[slot], 2 * H + cq, a.r0);
+        tma_load_2d(s + 5 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], 2 * H + cq, a.r0);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
+      bool ok = true;
+      for (int it = 0; it <= n_it && ok; ++it) {
+        if (it < n_it) {  // ---- S and R of item `it`
+          const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+          const int slot = it % ATC_SLOTS;
+          if (!mbar_wait(&kv_full[slot], (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
+          if (!mbar_wait(sr_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 303); break; }
+          tc_fence_after();
+          const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
+          const uint32_t q_hi = s0, q_lo = s0 + ATC_PLANE_BYTES, k_hi = s0 + 2 * ATC_PLANE_BYTES, k_lo = s0 + 3 * ATC_PLANE_BYTES;
+          const uint32_t id_s = umma_idesc_f16(a.nk32), id_r = umma_idesc_f16(a.nk32 + a.nr32);
+          const uint32_t e_off = (uint32_t)(128 - a.nk32) * 64u;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ko = ks * 32;  // bytes inside the 64-byte swizzle row
+            const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
+            umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, ks);
+            umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_lo + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
+            umma_f16(tmem + ATC_COL_S, dq_lo, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ko = ks * 32;
+            const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
+            umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, ks);
+            umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_lo_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
+            umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
+          }
+          umma_commit(sr_full);
+        }
+        if (it > 0) {  // ---- O = P V of item `it - 1`, 64 keys per round
+          const int j = it - 1, slot = j % ATC_SLOTS;
+          const AtcItem a = atc_item(j, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+          const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
+          const uint32_t v_hi = s0 + 4 * ATC_PLANE_BYTES, v_lo = s0 + 5 * ATC_PLANE_BYTES;
+          if (!mbar_wait(o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
+          for (int r = 0; r < 2 && ok; ++r) {
+            if (!mbar_wait(&p_full[r], (uint32_t)(j & 1))) { atomicExch(err_flag, 305); ok = false; break; }
+            tc_fence_after();
+            const int nks = min(4, (a.nk32 - 64 * r) >> 4);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint32_t vb = (uint32_t)(64 * r + 16 * ks) * 64u;
+              const uint32_t p_hi = tmem + ATC_COL_P + 8 * ks, p_lo = tmem + ATC_COL_P + 32 + 8 * ks;
+              umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
+              umma_f16_ts(tmem + ATC_COL_O, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+              umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+            }
+            umma_commit(&p_empty[r]);
+          }
+          umma_commit(o_full);
+          umma_commit(&kv_empty[slot]);
+        }
+      }
+    }
+  }
+  } else {
+    // ===================== softmax warpgroups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wg = warp >> 2, quad = warp & 3;  // TMEM lanes [32 quad, 32 quad + 32) are this warp's
+    const int row = quad * 32 + lane;                 // query row == TMEM lane
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    float* srow = scr + (size_t)row * ATC_SCR_PITCH;
+    const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
+    for (int it = wg; it < n_it; it += 2) {
+      const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+      const bool active = quad * 32 < a.n_rows;
+      const uint32_t par = (uint32_t)(it & 1);
+      float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
+      uint32_t su[128];
+      if (!mbar_wait(sr_full, par)) { if (lane == 0) atomicExch(err_flag, 306); break; }
+      tc_fence_after();
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 32 < a.nk32) tmem_ld32_issue(t_lane + ATC_COL_S + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
+        tmem_ld_wait();
+        if (DBG && drow) {
+#pragma unroll
+          for (int k = 0; k < 128; ++k) if (k < a.nk32) drow[k] = __uint_as_float(su[k]);
+        }
+        // ---- skew: S[l, 32 c + i] += R[l, 32 (quad - c) + nk32 - 32 + (lane - i + 31)]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < a.nk32) {
+            const uint32_t cb = (uint32_t)(32 * (quad - c) + a.nk32 - 32);
+            uint32_t v[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tmem_ld32(t_lane + ATC_COL_R + cb + 32 * h, v);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(srow + 32 * h + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            const float* win = srow + lane + 31;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) su[32 * c + i] = __float_as_uint(__uint_as_float(su[32 * c + i]) + win[-i]);
+          }
+        }
+        if (DBG && drow) {
+#pragma unroll
+          for (int k = 0; k < 128; ++k) if (k < a.nk32) drow[128 + k] = __uint_as_float(su[k]);
+        }
+      }
+      tc_fence_before();  // every TMEM read of S / R by this warp has completed (tcgen05.wait::ld above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sr_empty);
+
+      // ---- scale, bias / mask, row max (log2 units)
+      float m = -INFINITY, sum = 0.0f;
+      if (active) {
+        const float* kb = key_bias ? key_bias + (size_t)a.chain * n_pad : nullptr;
+#pragma unroll
+        for (int k = 0; k < 128; ++k) {
+          if (k < a.nk32) {
+            float t = __uint_as_float(su[k]) * c_scale;
+            if (kb && k < a.n_keys) t = fmaf(kb[k], 1.44269504088896340736f, t);
+            t = k < a.n_keys ? t : -INFINITY;
+            su[k] = __float_as_uint(t);
+            m = fmaxf(m, t);
+          }
+        }
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 128; k += 4) {
+          if (k < a.nk32) {
+            const float p0 = ex2_approx(__uint_as_float(su[k]) - m), p1 = ex2_approx(__uint_as_float(su[k + 1]) - m);
+            const float p2 = ex2_approx(__uint_as_float(su[k + 2]) - m), p3 = ex2_approx(__uint_as_float(su[k + 3]) - m);
+            su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
+            su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
+            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          }
+        }
+        sum = (s0 + s1) + (s2 + s3);
+      }
+      // ---- P as fp16 hi / lo planes into TMEM, 64 keys per round
+      bool ok = true;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        // round 0 reuses the buffer the previous item's round 1 read; round 1 the one this item's round 0 read
+        if (!mbar_wait(&p_empty[r ^ 1], r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
+        tc_fence_after();
+        if (active && 64 * r < a.nk32) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {  // 32 keys -> 16 packed columns per plane
+            if (64 * r + 32 * g < a.nk32) {
+              uint32_t ph[16], pl[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                split2(__uint_as_float(su[64 * r + 32 * g + 2 * q]), __uint_as_float(su[64 * r + 32 * g + 2 * q + 1]), ph[q], pl[q]);
+              tmem_st16(t_lane + ATC_COL_P + 16 * g, ph);
+              tmem_st16(t_lane + ATC_COL_P + 32 + 16 * g, pl);
+            }
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[r]);
+      }
+      if (!ok) break;
+      // ---- O: normalise and store ctx as hi / lo planes
+      if (!mbar_wait(o_full, par)) { if (lane == 0) atomicExch(err_flag, 308); break; }
+      tc_fence_after();
+      uint32_t o[32];
+      if (active) tmem_ld32(t_lane + ATC_COL_O, o);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (active && row < a.n_rows) {
+        const float inv = 1.0f / sum;
+        if (DBG && drow) {
+#pragma unroll
+          for (int d = 0; d < 32; ++d) drow[256 + d] = __uint_as_float(o[d]);
+          drow[288] = m; drow[289] = sum;
+        }
+        uint32_t oh[16], ol[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          split2(__uint_as_float(o[2 * q]) * inv, __uint_as_float(o[2 * q + 1]) * inv, oh[q], ol[q]);
+        const size_t off = (size_t)(a.r0 + row) * H + a.head * FD_HEAD_DIM;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(ctx_hi + off + 8 * q) = make_uint4(oh[4 * q], oh[4 * q + 1], oh[4 * q + 2], oh[4 * q + 3]);
+          *reinterpret_cast<uint4*>(ctx_lo + off + 8 * q) = make_uint4(ol[4 * q], ol[4 * q + 1], ol[4 * q + 2], ol[4 * q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// FOLDINGDIFF_B200_ATT: "tc" = this kernel, "groups" = attention_mma.cuh, anything else = attention_pool.cuh.
+inline bool atc_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FOLDINGDIFF_B200_ATT");
+    on = (e && e[0] == 't') ? 1 : 0;
+  }
+  return on == 1;
+}
+inline float*& atc_debug_dump() {  // test hook: device buffer [items][128][ATC_DBG_ROW] or nullptr
+  static float* p = nullptr;
+  return p;
+}
+
+inline int atc_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const int* row_start, const int* n_rows,
+                      const int* n_keys, const float* key_bias, int n_pad, const __half* e_hi, const __half* e_lo, int H,
+                      int heads, int n_items, __half* ctx_hi, __half* ctx_lo, int sm_count, cudaStream_t st) {
+  static unsigned long long configured = 0;
+  static const AtcDesc dsc = atc_default_desc();
+  if (tc_need_configure(&configured) &&
+      (cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc_smem_bytes()) != cudaSuccess ||
+       cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc_smem_bytes()) != cudaSuccess))
+    return 10;
+  int* err = tc_err_flag();
+  if (!err) return 11;
+  const int grid = n_items < sm_count ? n_items : sm_count;
+  if (atc_debug_dump())
+    attention_tc_kernel<true><<<grid, ATC_THREADS, atc_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
+                                                                           n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
+                                                                           dsc, atc_debug_dump(), err);
+  else
+    attention_tc_kernel<false><<<grid, ATC_THREADS, atc_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
+                                                                            n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
+                                                                            dsc, nullptr, err);
+  return cudaGetLastError() == cudaSuccess ? 0 : 12;
+}
+
+}  // namespace fd

@@ -242,6 +242,12 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
  * MMA issuer / epilogue timed out (the kernels never spin forever). Negative = CUDA error. */
 int32_t fd_debug_tc_status(void);
 
+/* Debug / test hook for the tcgen05 attention kernel (FOLDINGDIFF_B200_ATT=tc): while dump_dev is
+ * non-NULL every launch also writes, per (chain, head) item and query row, 290 floats
+ * {S raw [128], S + relative-key term [128], O unnormalised [32], row max (log2 units), row sum} to
+ * dump_dev[(chain * heads + head) * 128 + row]. Pass NULL to switch the dump off again. */
+int32_t fd_debug_attention_dump(float* dump_dev);
+
 #ifdef __cplusplus
 }
 #endif
