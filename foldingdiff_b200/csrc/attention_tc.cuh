@@ -125,22 +125,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(scr + 128 * ATC_SCR_PITCH);
   uint64_t* kv_full = bars;                  // [3] TMA -> MMA
   uint64_t* kv_empty = bars + ATC_SLOTS;     // [3] MMA (commit) -> TMA
-  uint64_t* sr_full = bars + 2 * ATC_SLOTS;  // MMA -> softmax
-  uint64_t* sr_empty = sr_full + 1;          // softmax -> MMA
-  uint64_t* p_full = sr_full + 2;            // [2] softmax -> MMA, per 64-key round
-  uint64_t* p_empty = sr_full + 4;           // [2] MMA -> softmax
-  uint64_t* o_full = sr_full + 6;            // MMA -> softmax
-  uint64_t* o_empty = sr_full + 7;           // softmax -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 8);
+  // A barrier a warpgroup WAITS on must show it every phase: a waiter that only looks at every other phase cannot
+  // tell "two phases behind" from "done" by parity (warpgroup 1 would sail through its very first wait).  So the
+  // MMA -> softmax barriers exist once per warpgroup; the softmax -> MMA ones are seen in item order by the MMA warp.
+  uint64_t* sr_full = bars + 2 * ATC_SLOTS;  // [2] MMA -> softmax warpgroup (it & 1)
+  uint64_t* o_full = sr_full + 2;            // [2] MMA -> softmax warpgroup (it & 1)
+  uint64_t* sr_empty = sr_full + 4;          // softmax -> MMA
+  uint64_t* o_empty = sr_full + 5;           // softmax -> MMA
+  uint64_t* p_full = sr_full + 6;            // [2] softmax -> MMA, per 64-key round
+  uint64_t* p_empty = sr_full + 8;           // [2] MMA -> softmax, per round (see the waits for why parity is exact)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
 
   if (tid == 0) {
     for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(sr_full, 1); mbar_init(sr_empty, 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
-    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    mbar_init(sr_empty, 4); mbar_init(o_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
   }
@@ -212,7 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_lo_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
             umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
           }
-          umma_commit(sr_full);
+          umma_commit(&sr_full[it & 1]);
         }
         if (it > 0) {  // ---- O = P V of item `it - 1`, 64 keys per round
           const int j = it - 1, slot = j % ATC_SLOTS;
@@ -233,7 +237,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
             umma_commit(&p_empty[r]);
           }
-          umma_commit(o_full);
+          umma_commit(&o_full[j & 1]);
           umma_commit(&kv_empty[slot]);
         }
       }
@@ -250,10 +254,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     for (int it = wg; it < n_it; it += 2) {
       const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
       const bool active = quad * 32 < a.n_rows;
-      const uint32_t par = (uint32_t)(it & 1);
+      const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // item parity, per-warpgroup parity
       float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
       uint32_t su[128];
-      if (!mbar_wait(sr_full, par)) { if (lane == 0) atomicExch(err_flag, 306); break; }
+      if (!mbar_wait(&sr_full[wg], wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
       tc_fence_after();
       if (active) {
 #pragma unroll
@@ -322,7 +326,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       bool ok = true;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        // round 0 reuses the buffer the previous item's round 1 read; round 1 the one this item's round 0 read
+        // round 0 reuses the buffer the previous item's round 1 read; round 1 the one this item's round 0 read.
+        // Both barriers are shared by the two warpgroups; the parity test is still exact: phase it - 2 of
+        // p_empty[1] retired before this warpgroup's own o_full of item it - 2, and phase it - 1 of p_empty[0]
+        // retires (commit order) before phase it - 1 of p_empty[1], which was just waited for.
         if (!mbar_wait(&p_empty[r ^ 1], r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
         tc_fence_after();
         if (active && 64 * r < a.nk32) {
@@ -345,7 +352,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       }
       if (!ok) break;
       // ---- O: normalise and store ctx as hi / lo planes
-      if (!mbar_wait(o_full, par)) { if (lane == 0) atomicExch(err_flag, 308); break; }
+      if (!mbar_wait(&o_full[wg], wpar)) { if (lane == 0) atomicExch(err_flag, 308); break; }
       tc_fence_after();
       uint32_t o[32];
       if (active) tmem_ld32(t_lane + ATC_COL_O, o);
