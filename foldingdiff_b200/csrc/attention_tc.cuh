@@ -93,10 +93,50 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// explicit shared-space accesses for the skew scratch: through the generic pointer (the 1024-byte alignment
+// arithmetic hides the address space from the compiler) they compile to LD.E / ST.E
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-struct AtcItem {
-  int chain, head, r0, n_rows, n_keys, nk32, nr32;
+// mbarrier helpers on shared-space addresses (computed once per thread).  The wait passes a suspend-time hint:
+// ncu on the first version showed 37% of all issued instructions were try_wait spin iterations of parked warps.
+__device__ __forceinline__ bool atc_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(100000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool atc_wait(uint32_t bar, uint32_t parity) {  // bounded like mbar_wait (~2 s)
+  if (atc_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!atc_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void atc_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void atc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct AtcItem {  // raw loads only: the derived sizes are computed at the point of use, so a descriptor fetched one
+  int chain, head, r0, n_rows, n_keys;  // iteration ahead never stalls the iteration that issued its loads
+  __device__ __forceinline__ int nk32() const { return (n_keys + 31) & ~31; }
+  __device__ __forceinline__ int nr32() const { return (n_rows + 31) & ~31; }
 };
 __device__ __forceinline__ AtcItem atc_item(int it, int n_items, int heads, const int* __restrict__ row_start,
                                             const int* __restrict__ n_rows_arr, const int* __restrict__ n_keys_arr) {
@@ -104,7 +144,6 @@ __device__ __forceinline__ AtcItem atc_item(int it, int n_items, int heads, cons
   const int item = n_items - 1 - ((int)blockIdx.x + it * (int)gridDim.x);  // batches are length-sorted: long first
   a.chain = item / heads; a.head = item % heads;
   a.r0 = row_start[a.chain]; a.n_rows = n_rows_arr[a.chain]; a.n_keys = n_keys_arr[a.chain];
-  a.nk32 = (a.n_keys + 31) & ~31; a.nr32 = (a.n_rows + 31) & ~31;
   return a;
 }
 
@@ -134,14 +173,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   uint64_t* o_empty = sr_full + 5;           // softmax -> MMA
   uint64_t* p_full = sr_full + 6;            // [2] softmax -> MMA, per 64-key round
   uint64_t* p_empty = sr_full + 8;           // [2] MMA -> softmax, per round (see the waits for why parity is exact)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 10);
+  uint64_t* s_empty = sr_full + 10;          // softmax -> MMA: S sits in registers (R is released later, by sr_empty)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
 
   if (tid == 0) {
     for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(sr_empty, 4); mbar_init(o_empty, 4);
+    mbar_init(sr_empty, 4); mbar_init(o_empty, 4); mbar_init(s_empty, 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
     }
@@ -161,6 +201,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // shared-space addresses of the barriers (8 bytes each, same order as above)
+  const uint32_t b_kv_full = smem_u32(kv_full), b_kv_empty = smem_u32(kv_empty), b_sr_full = smem_u32(sr_full);
+  const uint32_t b_o_full = smem_u32(o_full), b_sr_empty = smem_u32(sr_empty), b_o_empty = smem_u32(o_empty);
+  const uint32_t b_p_full = smem_u32(p_full), b_p_empty = smem_u32(p_empty), b_s_empty = smem_u32(s_empty);
 
   // register reallocation between the warpgroups (pool = 384 x 168): producers keep 40, softmax threads get 232 -
   // one query row is 128 fp32 logits plus the fp16 hi / lo staging, which does not fit the static 168
@@ -169,10 +213,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
       for (int it = 0; it < n_it; ++it) {
         const int slot = it % ATC_SLOTS, use = it / ATC_SLOTS;
-        const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
-        if (!mbar_wait(&kv_empty[slot], (uint32_t)((use & 1) ^ 1))) { atomicExch(err_flag, 301); break; }
+        const AtcItem a = nxt;
+        if (it + 1 < n_it) nxt = atc_item(it + 1, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+        if (!atc_wait(b_kv_empty + 8 * slot, (uint32_t)((use & 1) ^ 1))) { atomicExch(err_flag, 301); break; }
         uint8_t* s = ring + (size_t)slot * ATC_SLOT_BYTES;
         const int cq = a.head * FD_HEAD_DIM;
         mbar_expect_tx(&kv_full[slot], ATC_SLOT_BYTES);
@@ -189,17 +235,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     if (lane == 0) {
       const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
       bool ok = true;
+      // item descriptors one iteration ahead: their (dependent) global loads stay off the issue path
+      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr), cur = nxt, prev = nxt;
       for (int it = 0; it <= n_it && ok; ++it) {
+        prev = cur; cur = nxt;
+        if (it + 1 < n_it) nxt = atc_item(it + 1, n_items, heads, row_start, n_rows_arr, n_keys_arr);
         if (it < n_it) {  // ---- S and R of item `it`
-          const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+          const AtcItem a = cur;
+          const int nk32 = a.nk32(), nr32 = a.nr32();
           const int slot = it % ATC_SLOTS;
-          if (!mbar_wait(&kv_full[slot], (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
-          if (!mbar_wait(sr_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 303); break; }
+          if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
+          if (!atc_wait(b_s_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 309); break; }
           tc_fence_after();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t q_hi = s0, q_lo = s0 + ATC_PLANE_BYTES, k_hi = s0 + 2 * ATC_PLANE_BYTES, k_lo = s0 + 3 * ATC_PLANE_BYTES;
-          const uint32_t id_s = umma_idesc_f16(a.nk32), id_r = umma_idesc_f16(a.nk32 + a.nr32);
-          const uint32_t e_off = (uint32_t)(128 - a.nk32) * 64u;
+          const uint32_t id_s = umma_idesc_f16(nk32), id_r = umma_idesc_f16(nk32 + nr32);
+          const uint32_t e_off = (uint32_t)(128 - nk32) * 64u;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t ko = ks * 32;  // bytes inside the 64-byte swizzle row
@@ -208,6 +259,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_lo + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
             umma_f16(tmem + ATC_COL_S, dq_lo, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
           }
+          if (!atc_wait(b_sr_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 303); break; }
+          tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t ko = ks * 32;
@@ -216,18 +269,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_lo_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
             umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
           }
-          umma_commit(&sr_full[it & 1]);
+          atc_commit(b_sr_full + 8 * (it & 1));
         }
         if (it > 0) {  // ---- O = P V of item `it - 1`, 64 keys per round
           const int j = it - 1, slot = j % ATC_SLOTS;
-          const AtcItem a = atc_item(j, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+          const AtcItem a = prev;
+          const int nk32 = a.nk32();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t v_hi = s0 + 4 * ATC_PLANE_BYTES, v_lo = s0 + 5 * ATC_PLANE_BYTES;
-          if (!mbar_wait(o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
+          if (!atc_wait(b_o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
           for (int r = 0; r < 2 && ok; ++r) {
-            if (!mbar_wait(&p_full[r], (uint32_t)(j & 1))) { atomicExch(err_flag, 305); ok = false; break; }
+            if (!atc_wait(b_p_full + 8 * r, (uint32_t)(j & 1))) { atomicExch(err_flag, 305); ok = false; break; }
             tc_fence_after();
-            const int nks = min(4, (a.nk32 - 64 * r) >> 4);
+            const int nks = min(4, (nk32 - 64 * r) >> 4);
             for (int ks = 0; ks < nks; ++ks) {
               const uint32_t vb = (uint32_t)(64 * r + 16 * ks) * 64u;
               const uint32_t p_hi = tmem + ATC_COL_P + 8 * ks, p_lo = tmem + ATC_COL_P + 32 + 8 * ks;
@@ -235,10 +289,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
               umma_f16_ts(tmem + ATC_COL_O, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
               umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
             }
-            umma_commit(&p_empty[r]);
+            atc_commit(b_p_empty + 8 * r);
           }
-          umma_commit(&o_full[j & 1]);
-          umma_commit(&kv_empty[slot]);
+          atc_commit(b_o_full + 8 * (j & 1));
+          atc_commit(b_kv_empty + 8 * slot);
         }
       }
     }
@@ -251,76 +305,115 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     float* srow = scr + (size_t)row * ATC_SCR_PITCH;
     const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
+    AtcItem nxt = atc_item(wg < n_it ? wg : 0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
     for (int it = wg; it < n_it; it += 2) {
-      const AtcItem a = atc_item(it, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+      const AtcItem a = nxt;
+      const int nk32 = a.nk32();
+      if (it + 2 < n_it) nxt = atc_item(it + 2, n_items, heads, row_start, n_rows_arr, n_keys_arr);  // in flight under this item
       const bool active = quad * 32 < a.n_rows;
       const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // item parity, per-warpgroup parity
       float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
       uint32_t su[128];
-      if (!mbar_wait(&sr_full[wg], wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
+      if (!atc_wait(b_sr_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
       tc_fence_after();
+      // All per-key work below is organised in 32-key chunks guarded by ONE warp-uniform test each; inside a chunk
+      // the code is straight-line (ncu on the first version: a branch per key cost a third of the kernel).
+      float m = -INFINITY, sum = 0.0f;
       if (active) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c * 32 < a.nk32) tmem_ld32_issue(t_lane + ATC_COL_S + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
+          if (c * 32 < nk32) tmem_ld32_issue(t_lane + ATC_COL_S + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
         tmem_ld_wait();
+      }
+      tc_fence_before();  // S is in registers: the next item's Q K^T may overwrite it while this one's skew reads R
+      __syncwarp();
+      if (lane == 0) atc_arrive(b_s_empty);
+      if (active) {
         if (DBG && drow) {
 #pragma unroll
-          for (int k = 0; k < 128; ++k) if (k < a.nk32) drow[k] = __uint_as_float(su[k]);
+          for (int k = 0; k < 128; ++k) if (k < nk32) drow[k] = __uint_as_float(su[k]);
         }
         // ---- skew: S[l, 32 c + i] += R[l, 32 (quad - c) + nk32 - 32 + (lane - i + 31)]
+        const uint32_t srow_s = smem_u32(srow), win_s = srow_s + 4u * (uint32_t)(lane + 31);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (c * 32 < a.nk32) {
-            const uint32_t cb = (uint32_t)(32 * (quad - c) + a.nk32 - 32);
-            uint32_t v[32];
+          if (c * 32 < nk32) {
+            const uint32_t cb = (uint32_t)(32 * (quad - c) + nk32 - 32);
+            uint32_t v0[32], v1[32];
+            tmem_ld32_issue(t_lane + ATC_COL_R + cb, v0);
+            tmem_ld32_issue(t_lane + ATC_COL_R + cb + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              tmem_ld32(t_lane + ATC_COL_R + cb + 32 * h, v);
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(srow + 32 * h + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < 8; ++q) {
+              sts_v4(srow_s + 16 * q, v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+              sts_v4(srow_s + 128 + 16 * q, v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
             }
-            const float* win = srow + lane + 31;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) su[32 * c + i] = __float_as_uint(__uint_as_float(su[32 * c + i]) + win[-i]);
+            for (int i = 0; i < 32; ++i)
+              su[32 * c + i] = __float_as_uint(__uint_as_float(su[32 * c + i]) + lds_f32(win_s - 4u * (uint32_t)i));
           }
         }
         if (DBG && drow) {
 #pragma unroll
-          for (int k = 0; k < 128; ++k) if (k < a.nk32) drow[128 + k] = __uint_as_float(su[k]);
+          for (int k = 0; k < 128; ++k) if (k < nk32) drow[128 + k] = __uint_as_float(su[k]);
         }
       }
       tc_fence_before();  // every TMEM read of S / R by this warp has completed (tcgen05.wait::ld above)
       __syncwarp();
-      if (lane == 0) mbar_arrive(sr_empty);
+      if (lane == 0) atc_arrive(b_sr_empty);
 
-      // ---- scale, bias / mask, row max (log2 units)
-      float m = -INFINITY, sum = 0.0f;
+      // ---- mask, row max on the raw logits, p = 2^((s - max) * log2e / sqrt(32)), row sum
       if (active) {
-        const float* kb = key_bias ? key_bias + (size_t)a.chain * n_pad : nullptr;
+        if (key_bias) {  // additive attention mask of the forward API, folded into the raw logits (x sqrt(32))
+          const float* kb = key_bias + (size_t)a.chain * n_pad;
 #pragma unroll
-        for (int k = 0; k < 128; ++k) {
-          if (k < a.nk32) {
-            float t = __uint_as_float(su[k]) * c_scale;
-            if (kb && k < a.n_keys) t = fmaf(kb[k], 1.44269504088896340736f, t);
-            t = k < a.n_keys ? t : -INFINITY;
-            su[k] = __float_as_uint(t);
-            m = fmaxf(m, t);
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < nk32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int k = 32 * c + i;
+                su[k] = __float_as_uint(fmaf(kb[min(k, a.n_keys - 1)], 5.65685424949238019521f, __uint_as_float(su[k])));
+              }
+            }
           }
         }
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < nk32) {
+            if (c * 32 + 32 > a.n_keys) {  // the chunk that holds the end of the chain: keys >= n_keys -> -inf
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                su[32 * c + i] = (32 * c + i < a.n_keys) ? su[32 * c + i] : 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(su[32 * c + i])); m1 = fmaxf(m1, __uint_as_float(su[32 * c + i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(su[32 * c + i + 2])); m3 = fmaxf(m3, __uint_as_float(su[32 * c + i + 3]));
+            }
+          }
+        }
+        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float neg = -m * c_scale;
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 128; k += 4) {
-          if (k < a.nk32) {
-            const float p0 = ex2_approx(__uint_as_float(su[k]) - m), p1 = ex2_approx(__uint_as_float(su[k + 1]) - m);
-            const float p2 = ex2_approx(__uint_as_float(su[k + 2]) - m), p3 = ex2_approx(__uint_as_float(su[k + 3]) - m);
-            su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
-            su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
-            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < nk32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const int k = 32 * c + i;
+              const float p0 = ex2_approx(fmaf(__uint_as_float(su[k]), c_scale, neg));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(su[k + 1]), c_scale, neg));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(su[k + 2]), c_scale, neg));
+              const float p3 = ex2_approx(fmaf(__uint_as_float(su[k + 3]), c_scale, neg));
+              su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
+              su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
+              s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+            }
           }
         }
         sum = (s0 + s1) + (s2 + s3);
+        m *= c_scale;  // (debug dump: row max in log2 units)
       }
       // ---- P as fp16 hi / lo planes into TMEM, 64 keys per round
       bool ok = true;
@@ -330,12 +423,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         // Both barriers are shared by the two warpgroups; the parity test is still exact: phase it - 2 of
         // p_empty[1] retired before this warpgroup's own o_full of item it - 2, and phase it - 1 of p_empty[0]
         // retires (commit order) before phase it - 1 of p_empty[1], which was just waited for.
-        if (!mbar_wait(&p_empty[r ^ 1], r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
+        if (!atc_wait(b_p_empty + 8 * (r ^ 1), r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
         tc_fence_after();
-        if (active && 64 * r < a.nk32) {
+        if (active && 64 * r < nk32) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {  // 32 keys -> 16 packed columns per plane
-            if (64 * r + 32 * g < a.nk32) {
+            if (64 * r + 32 * g < nk32) {
               uint32_t ph[16], pl[16];
 #pragma unroll
               for (int q = 0; q < 16; ++q)
@@ -348,17 +441,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[r]);
+        if (lane == 0) atc_arrive(b_p_full + 8 * r);
       }
       if (!ok) break;
       // ---- O: normalise and store ctx as hi / lo planes
-      if (!mbar_wait(&o_full[wg], wpar)) { if (lane == 0) atomicExch(err_flag, 308); break; }
+      if (!atc_wait(b_o_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 308); break; }
       tc_fence_after();
       uint32_t o[32];
       if (active) tmem_ld32(t_lane + ATC_COL_O, o);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      if (lane == 0) atc_arrive(b_o_empty);
       if (active && row < a.n_rows) {
         const float inv = 1.0f / sum;
         if (DBG && drow) {
