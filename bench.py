@@ -349,7 +349,7 @@ def main():
         gemm_tf = sum(gemm_flops.values()) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         att_ms = prof["attention"][0] / nprof
         att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
-        dominant = "projection GEMMs (tc_gemm_kernel / sgemm_tn_kernel)" if gemm_ms >= att_ms else "attention_simt_kernel"
+        dominant = "projection GEMMs (tc_gemm_kernel / sgemm_tn_kernel)" if gemm_ms >= att_ms else "relative-key attention (attention_tc_kernel / attention_simt_kernel)"
         dom_tf = gemm_tf if gemm_ms >= att_ms else att_tf
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": dom_tf / peak_tf, "peak_source": peak_src,

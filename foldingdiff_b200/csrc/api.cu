@@ -315,7 +315,7 @@ int32_t fd_num_weights(int32_t layers) { return FD_W_HEAD + FD_W_PER_LAYER * lay
 int32_t fd_abi_version(void) { return FD_ABI_VERSION; }
 
 const char* fd_build_info(void) {
-  return "foldingdiff_b200 sm_100a; gemm: fp32-simt, tcgen05-3x, tcgen05-1x; attention: fp32-simt, mma.sync-3x";
+  return "foldingdiff_b200 sm_100a; gemm: fp32-simt, tcgen05-3x, tcgen05-1x; attention: fp32-simt, tcgen05-3x, mma.sync-3x";
 }
 
 const char* fd_last_error(void) { return g_err.c_str(); }

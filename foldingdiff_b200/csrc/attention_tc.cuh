@@ -22,8 +22,8 @@
 // TMA, 64-byte swizzle, into a 3-slot ring.
 //
 // Warp roles (384 threads, one persistent CTA per SM):  warps 0..3 and 4..7 = two softmax warpgroups that take
-// alternate items, warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner (warps 10, 11 only pad the producer
-// warpgroup so that setmaxnreg can move its registers to the softmax threads).  TMEM (512 columns):
+// alternate items, warp 8 = TMA producer, warp 9 = S / R MMA issuer + TMEM owner, warp 10 = P V MMA issuer (warp 11
+// only pads the producer warpgroup so that setmaxnreg can move its registers to the softmax threads).  TMEM (512 columns):
 // S [0,128) | R [128,384) | P hi [384,416) lo [416,448) (64 keys per round) | O [448,480).  S and R are single
 // buffered: a warpgroup releases them as soon as its rows sit in registers (sr_empty), so the S/R MMAs of
 // item i+1 run under the softmax of item i, and P V of item i runs under the S/R load of item i+1.
@@ -143,7 +143,11 @@ __device__ __forceinline__ AtcItem atc_item(int it, int n_items, int heads, cons
   AtcItem a;
   const int item = n_items - 1 - ((int)blockIdx.x + it * (int)gridDim.x);  // batches are length-sorted: long first
   a.chain = item / heads; a.head = item % heads;
-  a.r0 = row_start[a.chain]; a.n_rows = n_rows_arr[a.chain]; a.n_keys = n_keys_arr[a.chain];
+  // asm volatile: issued HERE.  As plain __restrict__ loads the compiler sank them to their first use in the next
+  // iteration (ncu: 17% of the softmax warps' time was the L2 latency of these three words).
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(a.r0) : "l"(row_start + a.chain));
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(a.n_rows) : "l"(n_rows_arr + a.chain));
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(a.n_keys) : "l"(n_keys_arr + a.chain));
   return a;
 }
 
@@ -180,7 +184,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
 
   if (tid == 0) {
-    for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
     mbar_init(sr_empty, 4); mbar_init(o_empty, 4); mbar_init(s_empty, 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
@@ -234,14 +238,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
-      bool ok = true;
       // item descriptors one iteration ahead: their (dependent) global loads stay off the issue path
-      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr), cur = nxt, prev = nxt;
-      for (int it = 0; it <= n_it && ok; ++it) {
-        prev = cur; cur = nxt;
-        if (it + 1 < n_it) nxt = atc_item(it + 1, n_items, heads, row_start, n_rows_arr, n_keys_arr);
-        if (it < n_it) {  // ---- S and R of item `it`
-          const AtcItem a = cur;
+      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+      for (int it = 0; it < n_it; ++it) {
+        {  // ---- S and R of item `it`
+          const AtcItem a = nxt;
+          nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
           const int nk32 = a.nk32(), nr32 = a.nr32();
           const int slot = it % ATC_SLOTS;
           if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
@@ -270,11 +272,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
           }
           atc_commit(b_sr_full + 8 * (it & 1));
+          atc_commit(b_kv_empty + 8 * slot);  // this thread's half of the slot release (Q / K reads retired)
         }
-        if (it > 0) {  // ---- O = P V of item `it - 1`, 64 keys per round
-          const int j = it - 1, slot = j % ATC_SLOTS;
-          const AtcItem a = prev;
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== MMA issuer 2: O = P V =====================
+    // A thread of its own: with one issuer walking S/R(it), PV(it-1), S/R(it+1), ... in program order the S / R
+    // products of the next item queued behind the P hand-off of the previous one - on the softmax warpgroups'
+    // critical path (ncu: they spent most of their wait time on sr_full).
+    if (lane == 0) {
+      bool ok = true;
+      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+      for (int j = 0; j < n_it && ok; ++j) {
+        {  // ---- O = P V of item j, 64 keys per round
+          const int slot = j % ATC_SLOTS;
+          const AtcItem a = nxt;
+          nxt = atc_item(min(j + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
           const int nk32 = a.nk32();
+          if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((j / ATC_SLOTS) & 1))) { atomicExch(err_flag, 310); break; }
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t v_hi = s0 + 4 * ATC_PLANE_BYTES, v_lo = s0 + 5 * ATC_PLANE_BYTES;
           if (!atc_wait(b_o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
@@ -292,7 +308,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             atc_commit(b_p_empty + 8 * r);
           }
           atc_commit(b_o_full + 8 * (j & 1));
-          atc_commit(b_kv_empty + 8 * slot);
+          atc_commit(b_kv_empty + 8 * slot);  // the other half of the slot release (V reads retired)
         }
       }
     }
@@ -497,7 +513,7 @@ constexpr int ATC2_QK_BYTES = 4 * ATC_PLANE_BYTES, ATC2_V_BYTES = 2 * ATC_PLANE_
 constexpr size_t atc2_smem_bytes() {
   return (size_t)ATC2_QK_SLOTS * ATC2_QK_BYTES + (size_t)ATC2_V_SLOTS * ATC2_V_BYTES + 2 * ATT_E_TABLE * 64
          + (size_t)256 * ATC_SCR_PITCH * 4   // skew scratch: one thread-private row per thread of a pair
-         + 2 * 2 * 128 * 2 * 4               // row max / row sum exchange, per pair
+         + 2 * 2 * 2 * 128 * 2 * 4           // row max / row sum exchange, per pair, double buffered
          + 256 + 1024;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -532,8 +548,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   __half* Es_hi = reinterpret_cast<__half*>(v_ring + ATC2_V_SLOTS * ATC2_V_BYTES);
   __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
   float* scr = reinterpret_cast<float*>(Es_lo + ATT_E_TABLE * ATT_PITCH);
-  float* xch = scr + 256 * ATC_SCR_PITCH;  // [pair][max | sum][row][half]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 128 * 2);
+  float* xch = scr + 256 * ATC_SCR_PITCH;  // [pair][max | sum][buffer][row][half]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 2 * 128 * 2);
   uint64_t* qk_full = bars;            // [2] TMA -> MMA
   uint64_t* qk_empty = bars + 2;       // [2] MMA -> TMA (S / R products retired)
   uint64_t* v_full = bars + 4;         // [3] TMA -> MMA
@@ -542,10 +558,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   uint64_t* o_full = bars + 12;        // [2] MMA -> softmax pair (it & 1)
   uint64_t* s_empty = bars + 14;       // softmax -> MMA, 8 warps
   uint64_t* sr_empty = bars + 15;      // softmax -> MMA, 8 warps
-  uint64_t* o_empty = bars + 16;       // softmax -> MMA, 8 warps
-  uint64_t* p_full = bars + 17;        // [2] softmax half h -> MMA, 4 warps
-  uint64_t* p_empty = bars + 19;       // [2] MMA -> softmax
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* o_empty = bars + 16;       // [2] softmax pair -> MMA, 8 warps (O is double buffered, one per pair)
+  uint64_t* p_full = bars + 18;        // [2] softmax half h -> MMA, 4 warps
+  uint64_t* p_empty = bars + 20;       // [2] MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -556,7 +572,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    mbar_init(s_empty, 8); mbar_init(sr_empty, 8); mbar_init(o_empty, 8);
+    mbar_init(s_empty, 8); mbar_init(sr_empty, 8); mbar_init(&o_empty[0], 8); mbar_init(&o_empty[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
   }
@@ -578,7 +594,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   const uint32_t b_p_full = smem_u32(p_full), b_p_empty = smem_u32(p_empty);
 
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 16) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -606,13 +622,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       // ===================== MMA issuer =====================
       if (lane == 0) {
         const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
-        bool ok = true;
-        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr), cur = nxt, prev = nxt;
-        for (int it = 0; it <= n_it && ok; ++it) {
-          prev = cur; cur = nxt;
-          nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-          if (it < n_it) {  // ---- S and R of item `it`
-            const AtcItem a = cur;
+        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+        for (int it = 0; it < n_it; ++it) {
+          {  // ---- S and R of item `it`
+            const AtcItem a = nxt;
+            nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
             const int nk32 = a.nk32(), nr32 = a.nr32();
             const int qs = it % ATC2_QK_SLOTS;
             if (!atc_wait(b_qk_full + 8 * qs, (uint32_t)((it / ATC2_QK_SLOTS) & 1))) { atomicExch(err_flag, 403); break; }
@@ -643,13 +657,24 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
             atc_commit(b_sr_full + 8 * (it & 1));
             atc_commit(b_qk_empty + 8 * qs);
           }
-          if (it > 0) {  // ---- O = P V of item `it - 1`, round r = key half r
-            const int j = it - 1, vs = j % ATC2_V_SLOTS;
-            const int nk32 = prev.nk32();
+        }
+      }
+    } else if (warp == 18) {
+      // ===================== MMA issuer 2: O = P V (own thread, see version 1) =====================
+      if (lane == 0) {
+        bool ok = true;
+        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
+        for (int j = 0; j < n_it && ok; ++j) {
+          {  // ---- O = P V of item j, round r = key half r
+            const int vs = j % ATC2_V_SLOTS;
+            const AtcItem a = nxt;
+            nxt = atc_item(min(j + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
+            const int nk32 = a.nk32();
             const uint32_t s0 = smem_u32(v_ring + (size_t)vs * ATC2_V_BYTES);
             const uint32_t v_hi = s0, v_lo = s0 + ATC_PLANE_BYTES;
             if (!atc_wait(b_v_full + 8 * vs, (uint32_t)((j / ATC2_V_SLOTS) & 1))) { atomicExch(err_flag, 406); break; }
-            if (!atc_wait(b_o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 407); break; }
+            if (!atc_wait(b_o_empty + 8 * (j & 1), (uint32_t)(((j >> 1) & 1) ^ 1))) { atomicExch(err_flag, 407); break; }
+            const uint32_t t_o = tmem + ATC_COL_O + 32 * (j & 1);
             for (int r = 0; r < 2 && ok; ++r) {
               if (!atc_wait(b_p_full + 8 * r, (uint32_t)(j & 1))) { atomicExch(err_flag, 408); ok = false; break; }
               tc_fence_after();
@@ -657,9 +682,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
               for (int ks = 0; ks < nks; ++ks) {
                 const uint32_t vb = (uint32_t)(64 * r + 16 * ks) * 64u;
                 const uint32_t p_hi = tmem + ATC_COL_P + 8 * ks, p_lo = tmem + ATC_COL_P + 32 + 8 * ks;
-                umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
-                umma_f16_ts(tmem + ATC_COL_O, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
-                umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+                umma_f16_ts(t_o, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
+                umma_f16_ts(t_o, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+                umma_f16_ts(t_o, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
               }
               atc_commit(b_p_empty + 8 * r);
             }
@@ -671,13 +696,49 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     }
   } else {
     // ===================== softmax warps: pair = item parity, half = key half, quad = TMEM lane quadrant =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int wgi = warp >> 2, pair = wgi >> 1, half = wgi & 1, quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t srow_s = smem_u32(scr + (size_t)(half * 128 + row) * ATC_SCR_PITCH), win_s = srow_s + 4u * (uint32_t)(lane + 31);
-    const uint32_t xm_s = smem_u32(xch + (size_t)(pair * 2 + 0) * 256 + row * 2);  // [row][half] row max
-    const uint32_t xs_s = smem_u32(xch + (size_t)(pair * 2 + 1) * 256 + row * 2);  // [row][half] row sum
+    const uint32_t xm_s = smem_u32(xch + (size_t)(pair * 2 + 0) * 512 + row * 2);  // [buffer][row][half] row max
+    const uint32_t xs_s = smem_u32(xch + (size_t)(pair * 2 + 1) * 512 + row * 2);  // [buffer][row][half] row sum
+    // The output of an item is finished one iteration LATER (under the next item's P V hand-off): O is double
+    // buffered in TMEM (one buffer per pair), and the row sums cross the pair through the max-exchange barrier of
+    // the next item - so an item costs one named barrier and no wait for its own P V.
+    AtcItem pa = {0, 0, 0, 0, 0};
+    bool have_prev = false;
+    auto finish = [&](const AtcItem& q, uint32_t qpar, uint32_t xbuf) -> bool {  // epilogue of this pair's item q
+      if (!atc_wait(b_o_full + 8 * pair, qpar)) { if (lane == 0) atomicExch(err_flag, 412); return false; }
+      tc_fence_after();
+      const bool q_active = quad * 32 < q.n_rows;
+      uint32_t o[16];
+      if (q_active) tmem_ld16(t_lane + ATC_COL_O + 32 * pair + 16 * half, o);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) atc_arrive(b_o_empty + 8 * pair);
+      if (q_active && row < q.n_rows) {
+        const float tot = lds_f32(xs_s + 1024 * xbuf) + lds_f32(xs_s + 1024 * xbuf + 4);
+        const float inv = 1.0f / tot;
+        if (DBG && dbg) {
+          float* qrow = dbg + ((size_t)(q.chain * heads + q.head) * 128 + row) * ATC_DBG_ROW;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) qrow[256 + 16 * half + d] = __uint_as_float(o[d]);
+          if (half == 0) qrow[289] = tot;
+        }
+        uint32_t oh[8], ol[8];
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2)
+          split2(__uint_as_float(o[2 * q2]) * inv, __uint_as_float(o[2 * q2 + 1]) * inv, oh[q2], ol[q2]);
+        const size_t off = (size_t)(q.r0 + row) * H + q.head * FD_HEAD_DIM + 16 * half;
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+          *reinterpret_cast<uint4*>(ctx_hi + off + 8 * q2) = make_uint4(oh[4 * q2], oh[4 * q2 + 1], oh[4 * q2 + 2], oh[4 * q2 + 3]);
+          *reinterpret_cast<uint4*>(ctx_lo + off + 8 * q2) = make_uint4(ol[4 * q2], ol[4 * q2 + 1], ol[4 * q2 + 2], ol[4 * q2 + 3]);
+        }
+      }
+      return true;
+    };
     const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
     AtcItem nxt = atc_item(min(pair, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
     for (int it = pair; it < n_it; it += 2) {
@@ -686,7 +747,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       const int nk32 = a.nk32();
       const bool active = quad * 32 < a.n_rows;          // this warp's rows exist
       const bool kact = active && 64 * half < nk32;      // ... and its key half is not empty
-      const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);
+      const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // wpar also picks the exchange buffer
       float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
       uint32_t su[64];
       if (!atc_wait(b_sr_full + 8 * pair, wpar)) { if (lane == 0) atomicExch(err_flag, 409); break; }
@@ -764,9 +825,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           }
         }
       }
-      sts_f32(xm_s + 4 * half, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      atc_pair_sync(pair);
-      const float m = fmaxf(lds_f32(xm_s), lds_f32(xm_s + 4));
+      sts_f32(xm_s + 1024 * wpar + 4 * half, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      atc_pair_sync(pair);  // the pair's maxima of this item - and its sums of the previous one - are visible
+      const float m = fmaxf(lds_f32(xm_s + 1024 * wpar), lds_f32(xm_s + 1024 * wpar + 4));
       float sum = 0.0f;
       if (kact) {
         const float neg = -m * c_scale;
@@ -789,11 +850,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         }
         sum = (s0 + s1) + (s2 + s3);
       }
-      sts_f32(xs_s + 4 * half, sum);  // read after the second pair sync, below
+      sts_f32(xs_s + 1024 * wpar + 4 * half, sum);  // read by finish() of this item, after the NEXT item's pair sync
+      if (DBG && drow && half == 0) drow[288] = m * c_scale;
       // ---- P round `half`.  Both halves first wait for the previous item's round 1 to retire (exact by parity:
       // this pair's own o_full of item it - 2 came after it), then half 1 for this item's round 0 (commit order).
       if (!atc_wait(b_p_empty + 8, par ^ 1u)) { if (lane == 0) atomicExch(err_flag, 410); break; }
-      if (half == 1 && !atc_wait(b_p_empty, par)) { if (lane == 0) atomicExch(err_flag, 411); break; }
+      if (half == 1) {  // half 1 finishes the previous item while round 0 of this one goes through the tensor core
+        if (have_prev && !finish(pa, wpar ^ 1u, wpar ^ 1u)) break;
+        if (!atc_wait(b_p_empty, par)) { if (lane == 0) atomicExch(err_flag, 411); break; }
+      }
       tc_fence_after();
       if (kact) {
 #pragma unroll
@@ -812,34 +877,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) atc_arrive(b_p_full + 8 * half);
-      // ---- O: this half normalises and stores 16 of the 32 head dims
-      if (!atc_wait(b_o_full + 8 * pair, wpar)) { if (lane == 0) atomicExch(err_flag, 412); break; }
-      tc_fence_after();
-      uint32_t o[16];
-      if (active) tmem_ld16(t_lane + ATC_COL_O + 16 * half, o);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_o_empty);
-      atc_pair_sync(pair);  // both halves' sums are in shared memory
-      if (active && row < a.n_rows) {
-        const float tot = lds_f32(xs_s) + lds_f32(xs_s + 4);
-        const float inv = 1.0f / tot;
-        if (DBG && drow) {
-#pragma unroll
-          for (int d = 0; d < 16; ++d) drow[256 + 16 * half + d] = __uint_as_float(o[d]);
-          if (half == 0) { drow[288] = m * c_scale; drow[289] = tot; }
-        }
-        uint32_t oh[8], ol[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          split2(__uint_as_float(o[2 * q]) * inv, __uint_as_float(o[2 * q + 1]) * inv, oh[q], ol[q]);
-        const size_t off = (size_t)(a.r0 + row) * H + a.head * FD_HEAD_DIM + 16 * half;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          *reinterpret_cast<uint4*>(ctx_hi + off + 8 * q) = make_uint4(oh[4 * q], oh[4 * q + 1], oh[4 * q + 2], oh[4 * q + 3]);
-          *reinterpret_cast<uint4*>(ctx_lo + off + 8 * q) = make_uint4(ol[4 * q], ol[4 * q + 1], ol[4 * q + 2], ol[4 * q + 3]);
-        }
-      }
+      if (half == 0 && have_prev && !finish(pa, wpar ^ 1u, wpar ^ 1u)) break;
+      pa = a; have_prev = true;
+    }
+    if (have_prev) {  // the pair's last item: its sums need one more pair barrier
+      atc_pair_sync(pair);
+      const int last = pair + ((n_it - 1 - pair) & ~1);
+      finish(pa, (uint32_t)((last >> 1) & 1), (uint32_t)((last >> 1) & 1));
     }
   }
   tc_fence_before();
@@ -850,13 +894,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   }
 }
 
-// FOLDINGDIFF_B200_ATT: "tc" = version 2 above, "tc1" = version 1, "groups" = attention_mma.cuh, anything else =
-// attention_pool.cuh.
-inline int atc_version() {  // 0: not selected, 1: one thread per row ("tc1"), 2: two threads per row ("tc")
+// FOLDINGDIFF_B200_ATT: unset / "tc" = version 1 (default: the fastest measured), "tc2" = version 2, "pool" =
+// attention_pool.cuh, "groups" = attention_mma.cuh.
+inline int atc_version() {  // 1: one thread per row (default), 2: two threads per row ("tc2"), 0: an mma.sync kernel
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FOLDINGDIFF_B200_ATT");
-    v = (e && e[0] == 't') ? ((e[1] == 'c' && e[2] == '1') ? 1 : 2) : 0;
+    if (!e || !e[0] || (e[0] == 't' && e[1] == 'c' && e[2] != '2')) v = 1;
+    else if (e[0] == 't') v = 2;
+    else v = 0;  // "pool", "groups"
   }
   return v;
 }
