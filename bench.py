@@ -44,9 +44,10 @@ PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
 # FD_GEMM_TC_3X, CTA-pair mode): dram__bytes_read.sum + dram__bytes_write.sum per launch, and
 # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active.  Static annotations, not re-measured here.
 NCU_GEMM = {
-    "dram_bytes_per_launch": {"gemm_qkv": 224.9e6, "gemm_attn_out": 80.8e6, "gemm_ffn1": 154.9e6, "gemm_ffn2": 150.8e6},
-    "tensor_pipe_active_pct": {"gemm_qkv": 76.9, "gemm_attn_out": 65.9, "gemm_ffn1": 49.3, "gemm_ffn2": 79.2},
-    "source": "profiles/r01_gemm_ncu.md (FFN1 captured before the fast-GELU epilogue)",
+    "dram_bytes_per_launch": {"gemm_qkv": 226.2e6, "gemm_attn_out": 82.4e6, "gemm_ffn1": 155.6e6, "gemm_ffn2": 153.1e6},
+    "tensor_pipe_active_pct": {"gemm_qkv": 75.8, "gemm_attn_out": 66.2, "gemm_ffn1": 62.1, "gemm_ffn2": 79.5,
+                               "attention_tc": 18.6},
+    "source": "profiles/r01_gemm_ncu.md, profiles/r01_attention_tc_ncu.md",
 }
 FALLBACK_PEAK_TFLOPS = 1590.0  # /opt/skills/guides/B200_PROFILING.md fallback (burst)
 
