@@ -391,6 +391,35 @@ def main():
             nerf_line["cpu_structures_per_s_1core"] = 8 / (time.perf_counter() - t0)
             nerf_line["cpu_sample"] = "8 chains, oracle restatement of nerf.NERFBuilder (single core, as one pool worker)"
 
+    # ---- section 8f rank-2 row: output writers (csv.gz + PDB per chain), native batch call vs the reference's way ----
+    if rank == 0 and nerf_line is not None:
+        import shutil
+        import tempfile
+        from foldingdiff_b200 import writers as fwriters
+        tmp = tempfile.mkdtemp(prefix="fd_writers_")
+        try:
+            ang_h, xyz_h = ang.cpu().numpy(), xyz.cpu().numpy()
+            t0 = time.perf_counter()
+            fwriters.write_batch(lengths, angles=ang_h, feature_names=names, csv_paths=[f"{tmp}/g{i}.csv.gz" for i in range(B)],
+                                 coords=xyz_h, pdb_paths=[f"{tmp}/g{i}.pdb" for i in range(B)])
+            dt = time.perf_counter() - t0
+            wline = {"native_chains_per_s": B / dt, "files_per_chain": 2, "chains": B,
+                     "api": "foldingdiff_b200.writers.write_batch (fd_write_batch)", "host_threads": min(32, os.cpu_count() or 1)}
+            if world == 1 and not args.no_cpu_baseline:
+                import pandas as pd
+                from oracle import writers as owriters  # CPU baseline leg: DataFrame.to_csv + the PDB text restatement
+                t0 = time.perf_counter()
+                for i in range(16):
+                    pd.DataFrame(ang_h[i, : lengths[i]], columns=names).to_csv(f"{tmp}/ref{i}.csv.gz")
+                    with open(f"{tmp}/ref{i}.pdb", "w") as f:
+                        f.write(owriters.backbone_pdb_text(xyz_h[i, : 3 * lengths[i]]))
+                wline["cpu_chains_per_s_1core"] = 16 / (time.perf_counter() - t0)
+                wline["cpu_sample"] = "16 chains, DataFrame.to_csv(.csv.gz) + Python PDB text (single core, as one pool worker)"
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    else:
+        wline = None
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, args.cpu_steps, start_t, wrap_all)
@@ -408,7 +437,7 @@ def main():
                        "l2": "inputs larger than L2: ~1 GB of activations per reverse step, 1000 steps per pass",
                        "algorithmic_tflop_per_pass": flops_step * start_t / 1e12},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu_baseline, "next_rows": {"nerf": nerf_line},
+            "cpu_baseline": cpu_baseline, "next_rows": {"nerf": nerf_line, "writers": wline},
         }
         print(json.dumps(line))
     if world > 1:

@@ -17,7 +17,6 @@ import sys
 from pathlib import Path
 
 import numpy as np
-import pandas as pd
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -98,34 +97,36 @@ def main() -> None:
         torch.manual_seed(args.seed)
         sampled = sampling.sample(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
                                   history="full" if args.fullhistory else "final")
-    cols = train_dset.feature_names["angles"]
-    dfs = [pd.DataFrame(s[-1], columns=cols) for s in sampled]
-    angles_dir = outdir / "sampled_angles"
+    cols = list(train_dset.feature_names["angles"])
+    from foldingdiff_b200 import nerf as fnerf
+    from foldingdiff_b200 import writers
+    # outputs (reference tree, README.md:90-96): sampled_angles/generated_{i}.csv.gz (what DataFrame.to_csv writes),
+    # sampled_pdb/generated_{i}.pdb, plus sampled_coords.npz.  Formatting, gzip and file IO run in native threads
+    # (fd_write_batch) instead of one pandas / biotite round trip per chain in a process pool (bin/sample.py:105-128).
+    finals = [np.ascontiguousarray(s[-1], dtype=np.float32) for s in sampled]
+    lens = [len(f) for f in finals]
+    n_max = max(lens)
+    packed = np.zeros((len(finals), n_max, len(cols)), dtype=np.float32)
+    for i, f in enumerate(finals):
+        packed[i, : lens[i]] = f
+    angles_dir, pdb_dir = outdir / "sampled_angles", outdir / "sampled_pdb"
     os.makedirs(angles_dir, exist_ok=True)
-    for i, df in enumerate(dfs):
-        df.to_csv(angles_dir / f"generated_{i}.csv.gz")
+    os.makedirs(pdb_dir, exist_ok=True)
+    # backbone coordinates on the GPU (fd_nerf_build): (3 * length, 3) N/CA/C per chain
+    xyz = fnerf.build_backbone(torch.from_numpy(packed).to(args.device), lens, cols, center=True).cpu().numpy()
+    writers.write_batch(lens, angles=packed, feature_names=cols,
+                        csv_paths=[str(angles_dir / f"generated_{i}.csv.gz") for i in range(len(lens))],
+                        coords=xyz, pdb_paths=[str(pdb_dir / f"generated_{i}.pdb") for i in range(len(lens))])
+    np.savez_compressed(outdir / "sampled_coords.npz", **{f"generated_{i}": xyz[i, : 3 * lens[i]] for i in range(len(lens))})
     if args.fullhistory:
         hist_dir = angles_dir / "sample_history"
         for i, series in enumerate(sampled):
             d = hist_dir / f"generated_{i}"
             os.makedirs(d, exist_ok=True)
-            for t, snap in enumerate(series):
-                pd.DataFrame(snap, columns=cols).to_csv(d / f"generated_{i}_timestep_{t}.csv.gz")
-    # backbone coordinates on the GPU (fd_nerf_build): one npz with an (3 * length, 3) N/CA/C array per chain
-    from foldingdiff_b200 import nerf as fnerf
-    n_max = max(len(df) for df in dfs)
-    packed = torch.zeros((len(dfs), n_max, len(cols)), dtype=torch.float32)
-    for i, df in enumerate(dfs):
-        packed[i, : len(df)] = torch.from_numpy(df.to_numpy(dtype=np.float32))
-    xyz = fnerf.build_backbone(packed.to(args.device), [len(df) for df in dfs], cols, center=True).cpu().numpy()
-    np.savez_compressed(outdir / "sampled_coords.npz", **{f"generated_{i}": xyz[i, : 3 * len(df)] for i, df in enumerate(dfs)})
-    try:  # unchanged post-processing of the reference (NeRF + PDB), if that package is installed
-        from foldingdiff.angles_and_coords import create_new_chain_nerf  # type: ignore
-        os.makedirs(outdir / "sampled_pdb", exist_ok=True)
-        for i, df in enumerate(dfs):
-            create_new_chain_nerf(str(outdir / "sampled_pdb" / f"generated_{i}.pdb"), df)
-    except Exception as e:  # noqa: BLE001
-        logging.warning(f"PDB writing skipped (reference post-processing not importable: {e})")
+            snaps = np.ascontiguousarray(series, dtype=np.float32)  # (T, len, F)
+            writers.write_batch([snaps.shape[1]] * len(snaps), angles=snaps, feature_names=cols,
+                                csv_paths=[str(d / f"generated_{i}_timestep_{t}.csv.gz") for t in range(len(snaps))])
+    dfs = finals
     logging.info(f"Wrote {len(dfs)} sampled angle sets to {angles_dir}")
 
 

@@ -66,6 +66,11 @@ SIGNATURES = {
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fd_debug_tc_status": (C.c_int32, []),
     "fd_debug_attention_dump": (C.c_int32, [C.c_void_p]),
+    "fd_write_angles_csv_gz": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), C.c_char_p,
+                                           C.c_int32]),
+    "fd_write_backbone_pdb": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p]),
+    "fd_write_batch": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int32, C.c_int32]),
 }
 
 _lib: Optional[C.CDLL] = None

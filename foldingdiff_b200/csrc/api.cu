@@ -12,6 +12,7 @@
 #include "attention_mma.cuh"
 #include "attention_pool.cuh"
 #include "attention_tc.cuh"
+#include "writers.hpp"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
@@ -789,6 +790,47 @@ int32_t fd_nerf_build(const float* angles_dev, int32_t batch, int32_t n_pad, int
   cudaStreamSynchronize(st);  // d_len must outlive the kernel
   cudaFree(d_len);
   return rc;
+}
+
+// ---- output writers (host only) -------------------------------------------------
+int32_t fd_write_angles_csv_gz(const float* angles_host, int32_t n_rows, int32_t n_features, int32_t row_stride,
+                               const char* const* feature_names, const char* path, int32_t gz_level) {
+  if (!angles_host || !feature_names || !path) return fail(FD_ERR_INVALID, "null argument");
+  if (n_rows < 0 || n_features < 1 || row_stride < n_features) return fail(FD_ERR_INVALID, "bad shape");
+  const int rc = fdw::write_gz(path, fdw::angles_csv_text(angles_host, n_rows, n_features, row_stride, feature_names), gz_level);
+  return rc ? fail(FD_ERR_INVALID, "cannot write %s (%d)", path, rc) : FD_OK;
+}
+
+int32_t fd_write_backbone_pdb(const float* coords_host, int32_t n_atoms, const char* path) {
+  if (!coords_host || !path) return fail(FD_ERR_INVALID, "null argument");
+  if (n_atoms < 0 || n_atoms % 3 != 0) return fail(FD_ERR_INVALID, "expected 3N atoms (N, CA, C per residue), got %d", n_atoms);
+  if (n_atoms > 99999) return fail(FD_ERR_INVALID, "%d atoms do not fit the PDB serial field", n_atoms);
+  const int rc = fdw::write_text(path, fdw::backbone_pdb_text(coords_host, n_atoms));
+  return rc ? fail(FD_ERR_INVALID, "cannot write %s (%d)", path, rc) : FD_OK;
+}
+
+int32_t fd_write_batch(int32_t n_chains, const float* angles_host, int32_t n_pad, int32_t n_features,
+                       const char* const* feature_names, const float* coords_host, int32_t atoms_pad,
+                       const int32_t* lengths, const char* const* csv_paths, const char* const* pdb_paths,
+                       int32_t n_threads, int32_t gz_level) {
+  if (!lengths || n_chains < 0) return fail(FD_ERR_INVALID, "bad argument");
+  if (csv_paths && (!angles_host || !feature_names || n_features < 1 || n_pad < 1)) return fail(FD_ERR_INVALID, "csv output needs angles");
+  if (pdb_paths && (!coords_host || atoms_pad < 3)) return fail(FD_ERR_INVALID, "pdb output needs coordinates");
+  std::vector<fdw::BatchJob> jobs((size_t)n_chains);
+  for (int i = 0; i < n_chains; ++i) {
+    const int n = lengths[i];
+    if (n < 1 || (csv_paths && n > n_pad) || (pdb_paths && (3 * n > atoms_pad || 3 * n > 99999)))
+      return fail(FD_ERR_INVALID, "lengths[%d]=%d does not fit the padded arrays", i, n);
+    fdw::BatchJob& j = jobs[(size_t)i];
+    j.angles = csv_paths ? angles_host + (size_t)i * n_pad * n_features : nullptr;
+    j.n_rows = n; j.n_features = n_features; j.row_stride = n_features; j.names = feature_names;
+    j.csv_path = csv_paths ? csv_paths[i] : nullptr;
+    j.coords = pdb_paths ? coords_host + (size_t)i * atoms_pad * 3 : nullptr;
+    j.n_atoms = 3 * n;
+    j.pdb_path = pdb_paths ? pdb_paths[i] : nullptr;
+  }
+  const int bad = fdw::run_batch(jobs, n_threads, gz_level);
+  return bad ? fail(FD_ERR_INVALID, "%d output files could not be written", bad) : FD_OK;
 }
 
 int32_t fd_debug_tc_status(void) { return fd::tc_check_error(); }

@@ -237,6 +237,27 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
                            const int32_t* lengths, int32_t all_rows, const float* dist_dev, int32_t heads,
                            float* ctx_out_dev, void* stream);
 
+/* ---- output writers (host only, no device work) --------------------------------
+ * fd_write_angles_csv_gz: one chain's angle table as the gzip-compressed CSV pandas writes for a float32
+ *   DataFrame - replaces `s.to_csv(sampled_angles_folder / f"generated_{i}.csv.gz")`,
+ *   /root/reference/bin/sample.py:365-370: header ",name,name,..." , one "row_index,v,v,..." line per residue,
+ *   numbers spelled as numpy str(float32).  angles_host is [n_rows][row_stride] fp32, the first n_features
+ *   columns of each row are written.  gz_level 0..9 (pandas uses 9; -1 = zlib default).
+ * fd_write_backbone_pdb: N / CA / C backbone as PDB v3.3 ATOM records of GLY residues in chain A, occupancy
+ *   1.00, B factor 5.00 - replaces angles_and_coords.write_coords_to_pdb,
+ *   /root/reference/foldingdiff/angles_and_coords.py:187-253.  coords_host is [n_atoms][3] fp32, n_atoms = 3N.
+ * fd_write_batch: the per-chain fan-out of bin/sample.py:105-128 (multiprocessing.Pool + pandas / biotite) as
+ *   one call: chain i has lengths[i] residues, its angles at angles_host[i][n_pad][n_features] and its
+ *   coordinates at coords_host[i][atoms_pad][3]; csv_paths / pdb_paths give one file name per chain and either
+ *   may be NULL to skip that output.  Work is spread over n_threads host threads. */
+int32_t fd_write_angles_csv_gz(const float* angles_host, int32_t n_rows, int32_t n_features, int32_t row_stride,
+                               const char* const* feature_names, const char* path, int32_t gz_level);
+int32_t fd_write_backbone_pdb(const float* coords_host, int32_t n_atoms, const char* path);
+int32_t fd_write_batch(int32_t n_chains, const float* angles_host, int32_t n_pad, int32_t n_features,
+                       const char* const* feature_names, const float* coords_host, int32_t atoms_pad,
+                       const int32_t* lengths, const char* const* csv_paths, const char* const* pdb_paths,
+                       int32_t n_threads, int32_t gz_level);
+
 /* Debug / test hook: synchronise the current device and return (then clear) the tensor-core
  * pipeline error flag: 0 = healthy; 101..104 = a bounded mbarrier wait in the TMA producer /
  * MMA issuer / epilogue timed out (the kernels never spin forever). Negative = CUDA error. */
