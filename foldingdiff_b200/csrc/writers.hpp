@@ -69,17 +69,26 @@ inline int write_gz(const char* path, const std::string& text, int level) {
   return gzclose(f) == Z_OK ? 0 : 3;
 }
 
-// coords: [3 * n_res][3] (N, CA, C per residue), Angstrom.  PDB format v3.3 ATOM records, 80 columns.
+// coords: [3 * n_res][3] (N, CA, C per residue), Angstrom.  PDB format v3.3 ATOM records (80 columns) + CONECT.
 inline std::string backbone_pdb_text(const float* coords, int n_atoms) {
   static const char* kName[3] = {" N  ", " CA ", " C  "};
   static const char* kElem[3] = {" N", " C", " C"};
   std::string s;
-  s.reserve((size_t)n_atoms * 81 + 16);
+  s.reserve((size_t)n_atoms * 81 + (size_t)n_atoms / 3 * 34 + 16);
   char line[96];
   for (int i = 0; i < n_atoms; ++i) {
     const float* p = coords + (size_t)i * 3;
     const int n = snprintf(line, sizeof(line), "ATOM  %5d %s %3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s  \n", i + 1,
                            kName[i % 3], "GLY", 'A', i / 3 + 1, (double)p[0], (double)p[1], (double)p[2], 1.0, 5.0, kElem[i % 3]);
+    s.append(line, (size_t)n);
+  }
+  // the reference adds a single bond between consecutive atoms (angles_and_coords.py:236-240); biotite's PDB writer
+  // spells out only the inter-residue ones (C of residue i - N of residue i + 1), both directions, as CONECT records
+  // (golden file: plots/pdb_structures/noising_visualization/fully_noised.pdb of the reference)
+  for (int c = 3; c < n_atoms; c += 3) {
+    int n = snprintf(line, sizeof(line), "CONECT%5d%5d\n", c, c + 1);
+    s.append(line, (size_t)n);
+    n = snprintf(line, sizeof(line), "CONECT%5d%5d\n", c + 1, c);
     s.append(line, (size_t)n);
   }
   return s;

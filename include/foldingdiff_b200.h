@@ -244,7 +244,8 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
  *   numbers spelled as numpy str(float32).  angles_host is [n_rows][row_stride] fp32, the first n_features
  *   columns of each row are written.  gz_level 0..9 (pandas uses 9; -1 = zlib default).
  * fd_write_backbone_pdb: N / CA / C backbone as PDB v3.3 ATOM records of GLY residues in chain A, occupancy
- *   1.00, B factor 5.00 - replaces angles_and_coords.write_coords_to_pdb,
+ *   1.00, B factor 5.00, followed by CONECT records for the inter-residue C-N bonds (what biotite emits for the
+ *   reference's bond list) - replaces angles_and_coords.write_coords_to_pdb,
  *   /root/reference/foldingdiff/angles_and_coords.py:187-253.  coords_host is [n_atoms][3] fp32, n_atoms = 3N.
  * fd_write_batch: the per-chain fan-out of bin/sample.py:105-128 (multiprocessing.Pool + pandas / biotite) as
  *   one call: chain i has lengths[i] residues, its angles at angles_host[i][n_pad][n_features] and its

@@ -62,8 +62,9 @@ def test_pdb_matches_oracle_and_parses_back(tmp_path):
     assert writers.write_coords_to_pdb(xyz, p) == p
     text = open(p).read()
     assert text == owriters.backbone_pdb_text(xyz)
-    lines = text.splitlines()
+    lines = [l for l in text.splitlines() if l.startswith("ATOM")]
     assert len(lines) == 171 and all(len(l) == 80 for l in lines)
+    assert text.splitlines()[171:173] == ["CONECT    3    4", "CONECT    4    3"] and len(text.splitlines()) == 171 + 2 * 56
     parsed = np.array([[float(l[30:38]), float(l[38:46]), float(l[46:54])] for l in lines])
     assert np.abs(parsed - xyz).max() <= 5.1e-4
     assert [l[12:16] for l in lines[:3]] == [" N  ", " CA ", " C  "] and lines[3][22:26] == "   2" and lines[170][6:11] == "  171"
@@ -90,3 +91,23 @@ def test_batch_writer_equals_per_chain_calls(tmp_path):
         writers.write_batch([200], angles=ang[:1], feature_names=NAMES, csv_paths=[csvs[0]])  # longer than the padded array
     with pytest.raises(Exception):
         writers.write_batch([5], coords=xyz[:1], pdb_paths=[str(tmp_path / "no_such_dir" / "x.pdb")])
+
+
+def _atoms(path):
+    lines = open(path).read().splitlines()
+    atoms = [l for l in lines if l.startswith("ATOM")]
+    return np.array([[float(l[30:38]), float(l[38:46]), float(l[46:54])] for l in atoms], dtype=np.float32), lines
+
+
+def test_pdb_pinned_on_files_written_by_the_reference(tmp_path):
+    """tests/golden/ref_fully_noised.pdb was written by the reference's own write_coords_to_pdb (biotite) and is
+    committed in its repository (plots/pdb_structures/noising_visualization/fully_noised.pdb; res_id from 1 and
+    b_factor 5.00 as in angles_and_coords.py:200-232 - the sibling clean.pdb predates that code and is not used):
+    feeding its coordinates back through the native writer and the oracle must reproduce it byte for byte."""
+    from conftest import ROOT
+    gold = os.path.join(ROOT, "tests", "golden", "ref_fully_noised.pdb")
+    xyz, _ = _atoms(gold)
+    assert xyz.shape == (264, 3)
+    p = str(tmp_path / "a.pdb")
+    writers.write_coords_to_pdb(xyz, p)
+    assert open(p).read() == open(gold).read() == owriters.backbone_pdb_text(xyz)
