@@ -41,6 +41,31 @@ def test_production_shape_forward_matches_golden(gemm):
     assert err < FWD_TOL[gemm]
 
 
+def test_large_ragged_batch_every_cta_walks_many_items():
+    """400 chains x 12 heads = 4800 attention items on 148 persistent CTAs: every CTA pipelines ~32 items through its
+    TMA ring / TMEM buffers / mbarrier phases (the small cases above give each CTA at most one).  The tensor-core path
+    (tcgen05 GEMMs + tcgen05 attention) must agree with the fp32 CUDA-core path - independent kernels for every
+    contraction - and with the CPU oracle on a sample of chains."""
+    g = torch.Generator().manual_seed(4242)
+    lengths = [50 + (i * 7) % 79 for i in range(400)]
+    x = torch.randn(400, 128, 6, generator=g)
+    t = torch.randint(0, 1000, (400,), generator=g)
+    mask = prefix_mask(lengths, 128)
+    valid = mask.bool()
+    eps_tc = prod_model("tc3x")(x.cuda(), t.cuda(), attention_mask=mask.cuda()).cpu()
+    eps_32 = prod_model("fp32")(x.cuda(), t.cuda(), attention_mask=mask.cuda()).cpu()
+    err = float((eps_tc - eps_32)[valid].abs().max())
+    print(f"large batch: max|eps_tc3x - eps_fp32| over valid rows = {err:.3e}")
+    assert err < FWD_TOL["tc3x"]
+    from foldingdiff_b200 import _native
+    assert _native.lib().fd_debug_tc_status() == 0
+    pick = [0, 137, 399]
+    cfg = ofwd.OracleConfig(**synthetic.PRODUCTION)
+    oracle = ofwd.OracleModel(prod_state_dict(), cfg, [True] * 6).eval()
+    ref = oracle(x[pick], t[pick], attention_mask=mask[pick])
+    assert float((eps_tc[pick] - ref)[valid[pick]].abs().max()) < FWD_TOL["tc3x"]
+
+
 @pytest.mark.parametrize("gemm", GEMMS)
 def test_reference_invariances(mini_dir, gemm):
     """tests/test_transformer.py:83-162 of the reference: determinism, mask invariance, batch order."""
