@@ -45,7 +45,7 @@ constexpr int ATC_DBG_ROW = 128 + 128 + 32 + 2;      // floats per row of the de
 constexpr size_t atc_smem_bytes() {
   return (size_t)ATC_SLOTS * ATC_SLOT_BYTES + 2 * ATT_E_TABLE * 64   // ring + E hi / lo
          + (size_t)128 * ATC_SCR_PITCH * 4                           // skew scratch (one warpgroup at a time)
-         + 256 + 1024;                                               // barriers + alignment slack
+         + 512 + 1024;                                               // barriers + item descriptor ring + alignment slack
 }
 
 // Operand descriptors, high 32 bits (SBO | version 1 | layout type) - host-computed so a debug run can override
@@ -133,6 +133,13 @@ __device__ __forceinline__ void atc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_u32a(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+constexpr int ATC_META_RING = 8;  // item descriptors staged in shared memory by the TMA warp, 32 bytes each
+
 struct AtcItem {  // raw loads only: the derived sizes are computed at the point of use, so a descriptor fetched one
   int chain, head, r0, n_rows, n_keys;  // iteration ahead never stalls the iteration that issued its loads
   __device__ __forceinline__ int nk32() const { return (n_keys + 31) & ~31; }
@@ -179,6 +186,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   uint64_t* p_empty = sr_full + 8;           // [2] MMA -> softmax, per round (see the waits for why parity is exact)
   uint64_t* s_empty = sr_full + 10;          // softmax -> MMA: S sits in registers (R is released later, by sr_empty)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 11);
+  // Item descriptors {r0, n_rows, n_keys, head, chain}: the TMA warp, three items ahead of everyone, is the only role
+  // that reads them from global memory; it parks them in an 8-entry shared ring BEFORE arming the item's kv_full
+  // barrier, so every later role reads them with one LDS after a barrier it waits on anyway.  (ncu: with each role
+  // prefetching its own copy the compiler spilled the in-flight registers and stalled at the spill - ISETP / IMAD /
+  // BRA / STL long-scoreboard stalls were a quarter of the softmax warps' busy samples.)  An entry is rewritten 8
+  // items later, after kv_empty of item it + 5: both warpgroups have left item `it` by then.
+  int* meta = reinterpret_cast<int*>(bars) + 48;  // byte 192 of the 512-byte barrier block (barriers + TMEM slot end at 140)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
@@ -209,6 +223,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   const uint32_t b_kv_full = smem_u32(kv_full), b_kv_empty = smem_u32(kv_empty), b_sr_full = smem_u32(sr_full);
   const uint32_t b_o_full = smem_u32(o_full), b_sr_empty = smem_u32(sr_empty), b_o_empty = smem_u32(o_empty);
   const uint32_t b_p_full = smem_u32(p_full), b_p_empty = smem_u32(p_empty), b_s_empty = smem_u32(s_empty);
+  const uint32_t meta_s = smem_u32(meta);
+  auto meta_item = [&](int it) {  // valid once a barrier downstream of kv_full(it) has been waited for
+    const uint32_t m = meta_s + 32u * (uint32_t)(it & (ATC_META_RING - 1));
+    AtcItem a;
+    a.r0 = (int)lds_u32a(m); a.n_rows = (int)lds_u32a(m + 4); a.n_keys = (int)lds_u32a(m + 8);
+    a.head = (int)lds_u32a(m + 12); a.chain = (int)lds_u32a(m + 16);
+    return a;
+  };
 
   // register reallocation between the warpgroups (pool = 384 x 168): producers keep 40, softmax threads get 232 -
   // one query row is 128 fp32 logits plus the fp16 hi / lo staging, which does not fit the static 168
@@ -223,6 +245,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         const AtcItem a = nxt;
         if (it + 1 < n_it) nxt = atc_item(it + 1, n_items, heads, row_start, n_rows_arr, n_keys_arr);
         if (!atc_wait(b_kv_empty + 8 * slot, (uint32_t)((use & 1) ^ 1))) { atomicExch(err_flag, 301); break; }
+        {
+          int* m = meta + 8 * (it & (ATC_META_RING - 1));
+          m[0] = a.r0; m[1] = a.n_rows; m[2] = a.n_keys; m[3] = a.head; m[4] = a.chain;
+          __threadfence_block();  // ordered before the (releasing) expect_tx arrive below
+        }
         uint8_t* s = ring + (size_t)slot * ATC_SLOT_BYTES;
         const int cq = a.head * FD_HEAD_DIM;
         mbar_expect_tx(&kv_full[slot], ATC_SLOT_BYTES);
@@ -239,14 +266,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     if (lane == 0) {
       const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
       // item descriptors one iteration ahead: their (dependent) global loads stay off the issue path
-      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
       for (int it = 0; it < n_it; ++it) {
         {  // ---- S and R of item `it`
-          const AtcItem a = nxt;
-          nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-          const int nk32 = a.nk32(), nr32 = a.nr32();
           const int slot = it % ATC_SLOTS;
           if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
+          const AtcItem a = meta_item(it);
+          const int nk32 = a.nk32(), nr32 = a.nr32();
           if (!atc_wait(b_s_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 309); break; }
           tc_fence_after();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
@@ -283,14 +308,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     // critical path (ncu: they spent most of their wait time on sr_full).
     if (lane == 0) {
       bool ok = true;
-      AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
       for (int j = 0; j < n_it && ok; ++j) {
         {  // ---- O = P V of item j, 64 keys per round
           const int slot = j % ATC_SLOTS;
-          const AtcItem a = nxt;
-          nxt = atc_item(min(j + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-          const int nk32 = a.nk32();
           if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((j / ATC_SLOTS) & 1))) { atomicExch(err_flag, 310); break; }
+          const int nk32 = meta_item(j).nk32();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t v_hi = s0 + 4 * ATC_PLANE_BYTES, v_lo = s0 + 5 * ATC_PLANE_BYTES;
           if (!atc_wait(b_o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
@@ -321,17 +343,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     float* srow = scr + (size_t)row * ATC_SCR_PITCH;
     const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
-    AtcItem nxt = atc_item(wg < n_it ? wg : 0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
     for (int it = wg; it < n_it; it += 2) {
-      const AtcItem a = nxt;
-      const int nk32 = a.nk32();
-      if (it + 2 < n_it) nxt = atc_item(it + 2, n_items, heads, row_start, n_rows_arr, n_keys_arr);  // in flight under this item
-      const bool active = quad * 32 < a.n_rows;
       const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // item parity, per-warpgroup parity
-      float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
       uint32_t su[128];
       if (!atc_wait(b_sr_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
       tc_fence_after();
+      const AtcItem a = meta_item(it);
+      const int nk32 = a.nk32();
+      const bool active = quad * 32 < a.n_rows;
+      float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
       // All per-key work below is organised in 32-key chunks guarded by ONE warp-uniform test each; inside a chunk
       // the code is straight-line (ncu on the first version: a branch per key cost a third of the kernel).
       float m = -INFINITY, sum = 0.0f;
