@@ -147,25 +147,71 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
 _CPU_MODEL = None
+_REF = None  # (sampling, beta_schedules, utils) of the reference installed under baseline/_ref, or False
+
+
+def _reference():
+    """The UNMODIFIED reference from baseline/_ref (baseline/reference_arm.py), or False where it is not installed."""
+    global _REF
+    if _REF is None:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import reference_arm
+            _REF = reference_arm.load_reference()[:3] + (reference_arm,) if reference_arm.available() else False
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] baseline/_ref not usable ({e}); timing the oracle port instead", file=sys.stderr)
+            _REF = False
+    return _REF
+
+
+def cpu_kind():
+    return "reference" if _reference() else "port"
 
 
 def _cpu_model():
     global _CPU_MODEL
     if _CPU_MODEL is None:
-        from oracle import forward as ofwd  # the one place bench.py may execute oracle/
         sd = synthetic.synthetic_state_dict(synthetic.PRODUCTION, seed=0)
-        _CPU_MODEL = ofwd.OracleModel(sd, ofwd.OracleConfig(**synthetic.PRODUCTION), [True] * 6).eval()
+        ref = _reference()
+        if ref:
+            _CPU_MODEL = ref[3].build_model(sd, synthetic.PRODUCTION)
+        else:
+            from oracle import forward as ofwd  # the one place bench.py may execute oracle/
+            _CPU_MODEL = ofwd.OracleModel(sd, ofwd.OracleConfig(**synthetic.PRODUCTION), [True] * 6).eval()
     return _CPU_MODEL
 
 
 def _cpu_steps(sub, n_pad, T, start_t, steps, threads):
-    """seconds per reverse step of the oracle port on `threads` host threads (1 untimed warm-up step)."""
-    from oracle import loop as oloop
-    from oracle import schedules as osched
+    """
+    seconds per reverse step of the reference's CPU path on `threads` host threads (1 untimed warm-up step).
+    With baseline/_ref: the stock `sampling.p_sample` + per-column `utils.modulo_with_wrapped_range` + `.cpu()` of the
+    reference's loop body (sampling.py:111-131) around the reference-assembled model; otherwise the oracle port.
+    """
     torch.set_num_threads(threads)
     model = _cpu_model()
-    betas = osched.betas_for("cosine", T)
+    ref = _reference()
     g = torch.Generator().manual_seed(SEED)
+    if ref:
+        sampling, beta_schedules, utils = ref[:3]
+        betas = beta_schedules.get_variance_schedule("cosine", T)
+        x = torch.randn(len(sub), n_pad, 6, generator=g)
+
+        def step(img, i):
+            with torch.no_grad():
+                img = sampling.p_sample(model=model, x=img, t=torch.full((len(sub),), i, dtype=torch.long), seq_lens=sub,
+                                        t_index=i, betas=betas)
+            for j in range(img.shape[2]):
+                img[:, :, j] = utils.modulo_with_wrapped_range(img[:, :, j], range_min=-torch.pi, range_max=torch.pi)
+            img.cpu()
+            return img
+        x = step(x, start_t - 1)
+        t0 = time.perf_counter()
+        for k in range(steps):  # per-step cost does not depend on t
+            x = step(x, start_t - 2 - k)
+        return (time.perf_counter() - t0) / steps
+    from oracle import loop as oloop
+    from oracle import schedules as osched
+    betas = osched.betas_for("cosine", T)
     x = oloop.wrap(torch.randn(len(sub), n_pad, 6, generator=g))
     x = oloop.wrap(oloop.p_sample(model, x, torch.full((len(sub),), start_t - 1, dtype=torch.long), sub, betas))
     t0 = time.perf_counter()
@@ -194,7 +240,10 @@ def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
         _BEST_THREADS = min(probe, key=probe.get)
     dt = _cpu_steps(sub, n_pad, T, start_t, steps, _BEST_THREADS)
     rate = len(sub) / (dt * start_t)
-    sample = (f"{len(sub)} chains (every {stride}-th of the workload's lengths, sum len {sum(sub)}), {steps} reverse steps "
+    what = ("stock sampling.p_sample + wrap of the reference installed in baseline/_ref around its own GaussianFourierProjection / "
+            "BertEmbeddings / AnglesPredictor and the installed transformers' relative_key attention + BERT blocks (4.11.3 is "
+            "not installable); " if _reference() else "oracle port of the reference loop and forward (baseline/_ref absent); ")
+    sample = (what + f"{len(sub)} chains (every {stride}-th of the workload's lengths, sum len {sum(sub)}), {steps} reverse steps "
               f"timed after 1 warm-up at {dt:.3f} s/step on {_BEST_THREADS} threads (best of a 1-step probe; box has {cores} "
               f"cores), extrapolated x{start_t} steps")
     return rate, _BEST_THREADS, sample, dt
@@ -230,9 +279,13 @@ def main():
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dt * max(1, args.cpu_steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, "timesteps": T, "note": "CPU path: fp32 torch restatement of the reference forward "
-                       "(HF 4.11.3 encoder not installable) + the reference's loop arithmetic"},
-            "cpu_baseline": {"value": value, "unit": "backbones/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": wl_name, "timesteps": T,
+                       "note": ("CPU path: the unmodified reference installed in baseline/_ref - its own loop (sampling.p_sample), "
+                                "schedules, wrap and model sub-modules; encoder layers from the installed transformers' modules "
+                                "because transformers==4.11.3 is not installable (baseline/reference_arm.py)") if _reference() else
+                               ("CPU path: fp32 torch restatement of the reference forward (HF 4.11.3 encoder not "
+                                "installable) + the reference's loop arithmetic; baseline/_ref absent")},
+            "cpu_baseline": {"value": value, "unit": "backbones/s", "cores": cores, "kind": cpu_kind(), "sample": sample},
             "e2e": {"value": value, "unit": "backbones/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -423,7 +476,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, args.cpu_steps, start_t, wrap_all)
-        cpu_baseline = {"value": rate, "unit": "backbones/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu_baseline = {"value": rate, "unit": "backbones/s", "cores": cores, "kind": cpu_kind(), "sample": sample}
 
     if rank == 0:
         line = {
