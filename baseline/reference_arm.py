@@ -42,6 +42,14 @@ def load_reference():
     from oracle import ref_shims  # import-time stubs only
     ref_shims.REFERENCE_ROOT = REF_DIR
     ref_shims.install()
+    loaded = sys.modules.get("foldingdiff")
+    if loaded is not None and not os.path.realpath(getattr(loaded, "__file__", "") or "").startswith(os.path.realpath(REF_DIR)):
+        # the authoring container's tests may already have imported the same package from /root/reference
+        for name in [n for n in sys.modules if n == "foldingdiff" or n.startswith("foldingdiff.")]:
+            del sys.modules[name]
+    if REF_DIR in sys.path:
+        sys.path.remove(REF_DIR)
+    sys.path.insert(0, REF_DIR)
     from foldingdiff import beta_schedules, modelling, sampling, utils  # type: ignore
     assert os.path.realpath(sampling.__file__).startswith(os.path.realpath(REF_DIR)), sampling.__file__
     return sampling, beta_schedules, utils, modelling
