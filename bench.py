@@ -230,10 +230,16 @@ def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
     torch's CPU kernels do not scale to every core count, so the thread count is chosen by a one-step
     probe over {all cores, 64, 32, 16} and the best one is used ("all the host threads it can use").
     """
-    global _BEST_THREADS
+    global _BEST_THREADS, _REF, _CPU_MODEL
     cores = os.cpu_count() or 1
     stride = max(1, len(lengths) // chains)
     sub = [lengths[i] for i in range(0, len(lengths), stride)][:chains]
+    if _reference():
+        try:  # a reference install that imports but does not run must not cost the measurement: fall back to the port
+            _cpu_steps(sub[:2], n_pad, T, start_t, 1, min(cores, 16))
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] reference arm failed ({type(e).__name__}: {e}); timing the oracle port instead", file=sys.stderr)
+            _REF, _CPU_MODEL = False, None
     if _BEST_THREADS is None:
         cands = sorted({c for c in (cores, 64, 32, 16) if c <= cores}, reverse=True)
         probe = {c: _cpu_steps(sub, n_pad, T, start_t, 1, c) for c in cands}
