@@ -205,6 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
+    meta[8 * ATC_META_RING] = n_it;  // loop bound of the softmax warps, read back with LDS (one register less to spill)
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
   // the layer's distance table: 256 rows x 64 bytes per plane, 64-byte swizzle (same layout the TMA tiles have)
@@ -343,19 +344,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     float* srow = scr + (size_t)row * ATC_SCR_PITCH;
     const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
-    for (int it = wg; it < n_it; it += 2) {
+    // descriptor fields are re-read from the shared ring wherever they are used (an LDS each) instead of being kept
+    // in registers across the item: held live they were spilled, and the reloads missed L1 under the store traffic
+    auto fld = [&](int it, int k) { return (int)lds_u32a(meta_s + 32u * (uint32_t)(it & (ATC_META_RING - 1)) + 4u * (uint32_t)k); };
+#define ATC_ACTIVE(it) (quad * 32 < fld(it, 1))
+    for (int it = wg; it < (int)lds_u32a(meta_s + 32u * ATC_META_RING); it += 2) {  // n_it, parked behind the ring
       const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // item parity, per-warpgroup parity
       uint32_t su[128];
       if (!atc_wait(b_sr_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
       tc_fence_after();
-      const AtcItem a = meta_item(it);
-      const int nk32 = a.nk32();
-      const bool active = quad * 32 < a.n_rows;
-      float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
+      const int nk32 = (fld(it, 2) + 31) & ~31;
+      float* drow = (DBG && dbg) ? dbg + ((size_t)(fld(it, 4) * heads + fld(it, 3)) * 128 + row) * ATC_DBG_ROW : nullptr;
       // All per-key work below is organised in 32-key chunks guarded by ONE warp-uniform test each; inside a chunk
       // the code is straight-line (ncu on the first version: a branch per key cost a third of the kernel).
       float m = -INFINITY, sum = 0.0f;
-      if (active) {
+      if (ATC_ACTIVE(it)) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c * 32 < nk32) tmem_ld32_issue(t_lane + ATC_COL_S + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
@@ -364,7 +367,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       tc_fence_before();  // S is in registers: the next item's Q K^T may overwrite it while this one's skew reads R
       __syncwarp();
       if (lane == 0) atc_arrive(b_s_empty);
-      if (active) {
+      if (ATC_ACTIVE(it)) {
         if (DBG && drow) {
 #pragma unroll
           for (int k = 0; k < 128; ++k) if (k < nk32) drow[k] = __uint_as_float(su[k]);
@@ -375,14 +378,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         for (int c = 0; c < 4; ++c) {
           if (c * 32 < nk32) {
             const uint32_t cb = (uint32_t)(32 * (quad - c) + nk32 - 32);
-            uint32_t v0[32], v1[32];
-            tmem_ld32_issue(t_lane + ATC_COL_R + cb, v0);
-            tmem_ld32_issue(t_lane + ATC_COL_R + cb + 32, v1);
-            tmem_ld_wait();
+            // two 32-column pieces through ONE register array: with both in flight (64 registers next to the 128
+            // logits) loop invariants spilled, and their reloads miss L1 (ncu: 14 % local hit rate under the store
+            // traffic) - a tcgen05.ld + wait is 58 cycles (profiles/r01_tmem_latency.txt), an L2 round trip ten times that
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              sts_v4(srow_s + 16 * q, v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
-              sts_v4(srow_s + 128 + 16 * q, v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld32(t_lane + ATC_COL_R + cb + 32 * h, v);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) sts_v4(srow_s + 128 * h + 16 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -399,16 +403,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       if (lane == 0) atc_arrive(b_sr_empty);
 
       // ---- mask, row max on the raw logits, p = 2^((s - max) * log2e / sqrt(32)), row sum
-      if (active) {
+      if (ATC_ACTIVE(it)) {
+        const int n_keys = fld(it, 2);
         if (key_bias) {  // additive attention mask of the forward API, folded into the raw logits (x sqrt(32))
-          const float* kb = key_bias + (size_t)a.chain * n_pad;
+          const float* kb = key_bias + (size_t)fld(it, 4) * n_pad;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c * 32 < nk32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const int k = 32 * c + i;
-                su[k] = __float_as_uint(fmaf(kb[min(k, a.n_keys - 1)], 5.65685424949238019521f, __uint_as_float(su[k])));
+                su[k] = __float_as_uint(fmaf(kb[min(k, n_keys - 1)], 5.65685424949238019521f, __uint_as_float(su[k])));
               }
             }
           }
@@ -417,10 +422,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c * 32 < nk32) {
-            if (c * 32 + 32 > a.n_keys) {  // the chunk that holds the end of the chain: keys >= n_keys -> -inf
+            if (c * 32 + 32 > n_keys) {  // the chunk that holds the end of the chain: keys >= n_keys -> -inf
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                su[32 * c + i] = (32 * c + i < a.n_keys) ? su[32 * c + i] : 0xff800000u;
+                su[32 * c + i] = (32 * c + i < n_keys) ? su[32 * c + i] : 0xff800000u;
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -461,7 +466,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         // retires (commit order) before phase it - 1 of p_empty[1], which was just waited for.
         if (!atc_wait(b_p_empty + 8 * (r ^ 1), r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
         tc_fence_after();
-        if (active && 64 * r < nk32) {
+        if (ATC_ACTIVE(it) && 64 * r < nk32) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {  // 32 keys -> 16 packed columns per plane
             if (64 * r + 32 * g < nk32) {
@@ -484,11 +489,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       if (!atc_wait(b_o_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 308); break; }
       tc_fence_after();
       uint32_t o[32];
+      const bool active = ATC_ACTIVE(it);
       if (active) tmem_ld32(t_lane + ATC_COL_O, o);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) atc_arrive(b_o_empty);
-      if (active && row < a.n_rows) {
+      if (active && row < fld(it, 1)) {
         const float inv = 1.0f / sum;
         if (DBG && drow) {
 #pragma unroll
@@ -499,7 +505,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 #pragma unroll
         for (int q = 0; q < 16; ++q)
           split2(__uint_as_float(o[2 * q]) * inv, __uint_as_float(o[2 * q + 1]) * inv, oh[q], ol[q]);
-        const size_t off = (size_t)(a.r0 + row) * H + a.head * FD_HEAD_DIM;
+        const size_t off = (size_t)(fld(it, 0) + row) * H + fld(it, 3) * FD_HEAD_DIM;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           *reinterpret_cast<uint4*>(ctx_hi + off + 8 * q) = make_uint4(oh[4 * q], oh[4 * q + 1], oh[4 * q + 2], oh[4 * q + 3]);
@@ -552,6 +558,7 @@ __device__ __forceinline__ void atc_pair_sync(int pair) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+#undef ATC_ACTIVE
 
 template <bool DBG>
 __global__ void __launch_bounds__(ATC2_THREADS, 1)
