@@ -101,3 +101,40 @@ def test_forward_noising_item_equals_the_reference_item(ref, schedule):
         for k in a:
             va, vb = a[k], b[k]
             assert torch.equal(torch.as_tensor(va), torch.as_tensor(vb)), (k, idx, tval)
+
+
+def test_sample_orchestration_equals_stock_sample(ref, tmp_path, monkeypatch):
+    """
+    Row a1 (sampling.sample, sampling.py:135-224): length list, chunking, per-chunk noise draws, trimming, per-chain
+    slicing, mean-offset shift + re-wrap.  Both sides run the SAME inner loop (the stock p_sample_loop around the
+    reference-assembled model, on the CPU), so any difference comes from the orchestration: must be bit-identical.
+    """
+    import json
+    from conftest import mini_state_dict
+    from foldingdiff_b200 import sampling as ours
+    sd, cfg, _, _ = mini_state_dict()
+    model = reference_arm.build_model(sd, cfg)
+    d = tmp_path / "m"
+    d.mkdir()
+    (d / "training_args.json").write_text(json.dumps({"angles_definitions": "canonical-full-angles", "max_seq_len": 128}))
+    np.save(d / "training_mean_offset.npy", np.array([-1.47, 0.75, 3.1, 1.94, 2.03, 2.12]))  # the shift crosses +-pi for omega
+    T = 3
+    o_dset = datasets.NoisedAnglesDataset(datasets.AnglesEmptyDataset.from_dir(str(d)), timesteps=T, beta_schedule="cosine")
+    r_dset = ref["datasets"].NoisedAnglesDataset(ref["datasets"].AnglesEmptyDataset.from_dir(str(d)), timesteps=T, beta_schedule="cosine")
+    stock = ref["sampling"]
+
+    def stock_loop(model, lengths, noise, timesteps, betas, is_angle, disable_pbar=False, history="full"):
+        return stock.p_sample_loop(model, lengths, noise, timesteps, betas, is_angle=is_angle, disable_pbar=True)
+    monkeypatch.setattr(ours, "p_sample_loop", stock_loop)
+    for kw in (dict(n=2, sweep_lengths=(10, 14), batch_size=3), dict(n=1, sweep_lengths=(20, 23), batch_size=512)):
+        torch.manual_seed(77)
+        a = ours.sample(model, o_dset, **kw)
+        torch.manual_seed(77)
+        b = stock.sample(model, r_dset, disable_pbar=True, **kw)
+        assert len(a) == len(b) == kw["n"] * (kw["sweep_lengths"][1] - kw["sweep_lengths"][0])
+        for x, y in zip(a, b):
+            assert x.shape == y.shape == (T, x.shape[1], 6) and np.array_equal(x, y)
+    with pytest.raises(ValueError):
+        ours.sample(model, o_dset, n=1, sweep_lengths=(30, 30))
+    with pytest.raises(ValueError):
+        stock.sample(model, r_dset, n=1, sweep_lengths=(30, 30))
