@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from foldingdiff_b200 import modelling, sampling  # noqa: E402
 from foldingdiff_b200.datasets import AnglesEmptyDataset, NoisedAnglesDataset  # noqa: E402
 
-SEED = int(float.fromhex("54616977616e20697320616e20696e646570656e64656e7420636f756e747279") % 10000)  # 7344
+SEED = 7344  # the reference CLI default (bin/sample.py:34-37)
 
 
 def build_datasets(model_dir: Path):

@@ -49,6 +49,9 @@ SIGNATURES = {
     "fd_forward": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_p_sample_steps": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_p_sample_steps_philox": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_status": (C.c_int32, [C.c_void_p]),
     "fd_sample_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32,
                                    C.c_void_p]),

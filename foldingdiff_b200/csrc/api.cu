@@ -9,7 +9,6 @@
 #include <vector>
 
 #include "../../include/foldingdiff_b200.h"
-#include "attention_mma.cuh"
 #include "attention_pool.cuh"
 #include "attention_tc.cuh"
 #include "writers.hpp"
@@ -41,8 +40,19 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                     \
   } while (0)
 
+// Entry points make the handle's device current for their own duration only (the caller's current device is
+// restored on return, like any library that is handed explicit device pointers).
+struct DevGuard {
+  int prev = -1, want;
+  explicit DevGuard(int dev) : want(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+  }
+  ~DevGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+
 struct LayerW {
-  float *w_qkv, *b_qkv, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
+  float *w_qkv, *b_qkv, *b_qkv_tc = nullptr, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
   fd::TcWeight tq, to, ti, to2;  // tensor-core operand planes (hi / lo) of the four projections
   __half *e_hi = nullptr, *e_lo = nullptr;  // distance embedding as fp16 hi / lo, padded to 256 rows
 };
@@ -74,6 +84,9 @@ struct fd_handle {
   fd::TcActs tc;  // hi / lo operand planes of the activations (tensor-core modes)
   CUtensorMap att_hi, att_lo;  // per-head K / V boxes of the qkv planes (attention_pool.cuh)
   long long launches = 0;
+  // Device-side pipeline error flag (gemm_tc.cuh: bounded mbarrier waits), mirrored into pinned host memory by an
+  // async copy at the end of every forward / step window and checked at the next entry point and by fd_status().
+  int* host_flag = nullptr;
   // optional CUDA-event profiler (fd_profile_begin / fd_profile_end)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs: start, stop
@@ -135,10 +148,10 @@ void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stri
                   cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_EMBED, st);
-  fd::embed_kernel<VPL><<<blocks, 256, 0, st>>>(x, H->row_src, H->rows, H->n_pad, H->d.n_features,
-                                                H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps,
-                                                temb, temb_stride, H->h, planes ? planes->hi : nullptr,
-                                                (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : nullptr);
+  fd::launch_pdl(fd::embed_kernel<VPL>, dim3(blocks), dim3(256), 0, st, x, H->row_src, H->rows, H->n_pad, H->d.n_features,
+                 H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps, temb, temb_stride, H->h,
+                 planes ? planes->hi : (__half*)nullptr,
+                 (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : (__half*)nullptr);
   H->launches++;
 }
 
@@ -147,9 +160,9 @@ void launch_ln(fd_handle* H, const float* in, const float* resid, const float* g
                fd::TcPlane* planes, cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_LN, st);
-  fd::layernorm_kernel<VPL><<<blocks, 256, 0, st>>>(in, resid, H->rows, g, b, H->d.ln_eps, out,
-                                                    planes ? planes->hi : nullptr,
-                                                    (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : nullptr);
+  fd::launch_pdl(fd::layernorm_kernel<VPL>, dim3(blocks), dim3(256), 0, st, in, resid, H->rows, g, b, H->d.ln_eps, out,
+                 planes ? planes->hi : (__half*)nullptr,
+                 (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : (__half*)nullptr);
   H->launches++;
 }
 
@@ -186,47 +199,34 @@ void launch_attention(fd_handle* H, const float* dist, cudaStream_t st) {
 // tensor-core attention on the fp16 hi / lo planes (tc modes): qkv planes -> ctx planes
 int launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
   const int items = H->batch * H->d.heads;
-  const int want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS;
-  const int grid = want < H->sm_count ? want : H->sm_count;
-  const size_t smem = fd::att_smem_bytes();
   const float* bias = H->has_key_bias ? H->key_bias : nullptr;
   ProfScope ps(H, CAT_ATTN, st);
-  if (fd::atc_enabled() && H->gemm_mode == FD_GEMM_TC_3X) {
-    const int rc = fd::atc_launch(H->att_hi, H->att_lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
-                                  H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo, H->sm_count, st);
-    if (rc) return fail(FD_ERR_CUDA, "attention launch failed (%d)", rc);
-  } else if (fd::attp_enabled()) {
-    int rc;
-    if (H->gemm_mode == FD_GEMM_TC_3X)
-      rc = fd::attp_launch<true>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
-                                 H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
-                                 H->sm_count, st);
-    else
-      rc = fd::attp_launch<false>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
-                                  H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
-                                  H->sm_count, st);
-    if (rc) return fail(FD_ERR_CUDA, "attention launch failed (%d)", rc);
-  } else if (H->gemm_mode == FD_GEMM_TC_3X)
-    fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, smem, st>>>(
-        H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
-        H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
+  int rc;
+  if (H->gemm_mode == FD_GEMM_TC_3X && fd::atc_enabled())
+    rc = fd::atc_launch(H->att_hi, H->att_lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
+                        H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo, H->sm_count, st);
+  else if (H->gemm_mode == FD_GEMM_TC_3X)
+    rc = fd::attp_launch<true>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
+                               H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
+                               H->sm_count, st);
   else
-    fd::attention_mma_kernel<false><<<grid, fd::ATT_WARPS * 32, smem, st>>>(
-        H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias, H->n_pad, w.e_hi, w.e_lo,
-        H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo);
+    rc = fd::attp_launch<false>(H->att_hi, H->att_lo, H->tc.qkv.hi, H->tc.qkv.lo, H->row_start, H->n_rows, H->n_keys, bias,
+                                H->n_pad, w.e_hi, w.e_lo, H->d.hidden, H->d.heads, items, H->tc.ctx.hi, H->tc.ctx.lo,
+                                H->sm_count, st);
+  if (rc) return fail(FD_ERR_CUDA, "attention launch failed (%d)", rc);
   H->launches++;
   return FD_OK;
 }
 
 template <int VPL, bool SAMPLE>
-void launch_tail(fd_handle* H, float* eps_out, float* x, const float* z, float* hist,
+void launch_tail(fd_handle* H, float* eps_out, float* x, fd::StepNoise noise, float* hist,
                  fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st) {
   const int blocks = (H->rows * 32 + 255) / 256;
   const size_t smem = sizeof(float) * H->d.n_features * H->d.hidden;
   ProfScope ps(H, CAT_TAIL, st);
-  fd::tail_kernel<VPL, SAMPLE><<<blocks, 256, smem, st>>>(
-      H->tmp, H->row_src, H->rows, H->d.n_features, H->hln_g, H->hln_b, H->d.head_ln_eps, H->w_d2,
-      H->b_d2, eps_out, x, z, hist, coef, wrap_bits);
+  fd::launch_pdl(fd::tail_kernel<VPL, SAMPLE>, dim3(blocks), dim3(256), smem, st, (const float*)H->tmp,
+                 (const int*)H->row_src, H->rows, H->d.n_features, (const float*)H->hln_g, (const float*)H->hln_b,
+                 H->d.head_ln_eps, (const float*)H->w_d2, (const float*)H->b_d2, eps_out, x, noise, hist, coef, wrap_bits);
   H->launches++;
 }
 
@@ -269,7 +269,7 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
   launch_embed<VPL>(H, x, temb, temb_stride, tcm ? &H->tc.h : nullptr, st);
   for (int l = 0; l < H->d.layers; ++l) {
     LayerW& w = H->layers[l];
-    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, w.b_qkv, nullptr, tcm ? nullptr : H->qkv,
+    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, tcm ? w.b_qkv_tc : w.b_qkv, nullptr, tcm ? nullptr : H->qkv,
                      3 * Hd, Hd, &H->tc.h, tcm ? &H->tc.qkv : nullptr, st);
     if (rc) return rc;
     if (tcm) { rc = launch_attention_mma(H, w, st); if (rc) return rc; }
@@ -305,6 +305,29 @@ int check_launch() {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FD_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return FD_OK;
+}
+
+// The tcgen05 pipelines end with an error code instead of hanging when an mbarrier wait exceeds ~2 s (a preempted /
+// time-sliced GPU can do that).  Results of such a launch are garbage, so the code must reach the caller:
+//   flag_enqueue_copy  device flag -> the handle's pinned word, stream-ordered after the kernels just enqueued
+//   flag_poll          reports (and clears) a non-zero word: called on entry of every compute call, after the
+//                      synchronising calls, and by fd_status() once the caller has synchronised its stream
+int flag_enqueue_copy(fd_handle* h, cudaStream_t st) {
+  if (h->gemm_mode == FD_GEMM_FP32_SIMT || !h->host_flag) return FD_OK;
+  int* dflag = fd::tc_err_flag();
+  if (!dflag) return fail(FD_ERR_CUDA, "pipeline error flag unavailable");
+  FD_CUDA(cudaMemcpyAsync(h->host_flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return FD_OK;
+}
+int flag_poll(fd_handle* h) {
+  if (!h->host_flag) return FD_OK;
+  const int code = *(volatile int*)h->host_flag;
+  if (code == 0) return FD_OK;
+  *h->host_flag = 0;
+  int* dflag = fd::tc_err_flag();
+  if (dflag) cudaMemset(dflag, 0, sizeof(int));
+  return fail(FD_ERR_CUDA, "tensor-core pipeline timed out on device %d (stage code %d): the results of the previous "
+              "forward / step window are invalid", h->device, code);
 }
 
 }  // namespace
@@ -347,9 +370,15 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
   FD_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(FD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  FD_CUDA(cudaSetDevice(device));
+  DevGuard guard(device);
 
   fd_handle* h = new fd_handle();
+  if (cudaHostAlloc((void**)&h->host_flag, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    delete h;
+    return fail(FD_ERR_CUDA, "pinned status word: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *h->host_flag = 0;
+  if (!fd::tc_err_flag()) { cudaFreeHost(h->host_flag); delete h; return fail(FD_ERR_CUDA, "pipeline error flag allocation failed"); }
   h->d = d;
   h->device = device;
   h->gemm_mode = gemm_mode;
@@ -384,9 +413,16 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
   // tensor-core operand planes of the weights (prepared once; cheap)
   for (int l = 0; l < d.layers && !rc; ++l) {
     LayerW& w = h->layers[l];
-    if (fd::tc_pack_weight(w.w_qkv, 3 * H, H, &w.tq) || fd::tc_pack_weight(w.w_o, H, H, &w.to) ||
+    // the query rows of the fused QKV weight (and their bias) also carry the de-bias of the attention kernel's
+    // K = 32 products (gemm_tc.cuh: tc_split_weight_kernel)
+    if (fd::tc_pack_weight(w.w_qkv, 3 * H, H, &w.tq, H) || fd::tc_pack_weight(w.w_o, H, H, &w.to) ||
         fd::tc_pack_weight(w.w_i, I, H, &w.ti) || fd::tc_pack_weight(w.w_o2, H, I, &w.to2))
       rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc) rc = dev_alloc(h, (void**)&w.b_qkv_tc, sizeof(float) * 3 * H);
+    if (!rc) {
+      const fd::TcRz rz = fd::tc_rz();
+      fd::tc_scale_qbias_kernel<<<(3 * H + 255) / 256, 256>>>(w.b_qkv, w.b_qkv_tc, 3 * H, H, rz.alpha, rz.beta_att);
+    }
   }
   if (!rc && fd::tc_pack_weight(h->w_d1, H, H, &h->td1)) rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed");
   // distance embeddings as fp16 hi / lo planes, padded to 256 rows (row 2*max_pos-1.. are zero)
@@ -406,8 +442,6 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
   if (!rc) {
     cudaFuncSetAttribute(fd::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)attn_smem_bytes(128, 128));
-    cudaFuncSetAttribute(fd::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
-    cudaFuncSetAttribute(fd::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
     if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(FD_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (rc) {
@@ -420,7 +454,9 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
 
 void fd_destroy(fd_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DevGuard guard(h->device);
+  cudaDeviceSynchronize();  // the pinned status word may still be the target of an enqueued copy
+  if (h->host_flag) cudaFreeHost(h->host_flag);
   free_batch(h);
   for (auto& w : h->layers) { fd::tc_free_weight(&w.tq); fd::tc_free_weight(&w.to); fd::tc_free_weight(&w.ti); fd::tc_free_weight(&w.to2); }
   fd::tc_free_weight(&h->td1);
@@ -432,7 +468,7 @@ void fd_destroy(fd_handle* h) {
 int32_t fd_set_schedule(fd_handle* h, int32_t timesteps, const float* time_table, const float* coef) {
   if (!h || !time_table || !coef) return fail(FD_ERR_INVALID, "null argument");
   if (timesteps < 1) return fail(FD_ERR_INVALID, "timesteps=%d", timesteps);
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   FD_CUDA(cudaDeviceSynchronize());  // no step may still be reading the old table
   float* fresh = nullptr;
   FD_CUDA(cudaMalloc(&fresh, sizeof(float) * (size_t)timesteps * h->d.hidden));
@@ -465,7 +501,7 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
   if (batch < 1 || n_pad < 1 || n_pad > h->d.max_pos)
     return fail(FD_ERR_INVALID, "batch=%d n_pad=%d (max_pos=%d)", batch, n_pad, h->d.max_pos);
   cudaStream_t st = (cudaStream_t)stream;
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   std::vector<int> row_start(batch), n_rows(batch), n_keys(batch);
   long long rows = 0;
   for (int b = 0; b < batch; ++b) {
@@ -482,6 +518,9 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     for (int n = 0; n < n_rows[b]; ++n) row_src[row_start[b] + n] = b * n_pad + n;
 
   const int Hd = h->d.hidden, I = h->d.intermediate;
+  // no batch is installed until every allocation and copy below has succeeded: a failure part-way leaves the handle
+  // in the "fd_set_batch has not been called" state (FD_ERR_STATE), never pointing at freed or partial buffers
+  h->batch = 0; h->rows = 0; h->rows_pad = 0;
   if (batch > h->cap_batch || rows_pad > h->cap_rows || batch * n_pad > h->cap_bn) {
     FD_CUDA(cudaStreamSynchronize(st));
     free_batch(h);
@@ -506,7 +545,6 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     FD_CUDA(cudaMemsetAsync(h->ctx, 0, sizeof(float) * r * Hd, st));
     FD_CUDA(cudaMemsetAsync(h->a, 0, sizeof(float) * r * Hd, st));
   }
-  h->batch = batch; h->n_pad = n_pad; h->rows = (int)rows; h->rows_pad = rows_pad; h->all_rows = all_rows;
   FD_CUDA(cudaMemcpyAsync(h->row_src, row_src.data(), sizeof(int) * rows_pad, cudaMemcpyHostToDevice, st));
   FD_CUDA(cudaMemcpyAsync(h->row_start, row_start.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
   FD_CUDA(cudaMemcpyAsync(h->n_rows, n_rows.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, st));
@@ -518,6 +556,7 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     FD_CUDA(cudaMemcpyAsync(h->key_bias, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice, st));
   }
   // pageable-memory async copies have been staged by the time the call returns
+  h->batch = batch; h->n_pad = n_pad; h->rows = (int)rows; h->rows_pad = rows_pad; h->all_rows = all_rows;
   return FD_OK;
 }
 
@@ -526,15 +565,17 @@ int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, floa
   if (!h || !x_dev || !temb_dev || !eps_out_dev) return fail(FD_ERR_INVALID, "null argument");
   if (h->batch == 0) return fail(FD_ERR_STATE, "fd_set_batch has not been called");
   cudaStream_t st = (cudaStream_t)stream;
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
+  int rc = flag_poll(h);
+  if (rc) return rc;
   const int Hd = h->d.hidden;
   FD_CUDA(cudaMemsetAsync(eps_out_dev, 0, sizeof(float) * h->batch * h->n_pad * h->d.n_features, st));
-  int rc;
   fd::StepCoef none{};
-#define FD_FWD(V)                                                                                \
-  case V:                                                                                        \
-    rc = run_encoder<V>(h, x_dev, temb_dev, Hd, st);                                             \
-    if (!rc) launch_tail<V, false>(h, eps_out_dev, nullptr, nullptr, nullptr, none, 0u, st);     \
+  fd::StepNoise no_noise{nullptr, 0ull, 0ull};
+#define FD_FWD(V)                                                                                  \
+  case V:                                                                                          \
+    rc = run_encoder<V>(h, x_dev, temb_dev, Hd, st);                                               \
+    if (!rc) launch_tail<V, false>(h, eps_out_dev, nullptr, no_noise, nullptr, none, 0u, st);      \
     break;
   switch (Hd / 32) {
     FD_FWD(2) FD_FWD(4) FD_FWD(6) FD_FWD(8) FD_FWD(10) FD_FWD(12) FD_FWD(14) FD_FWD(16)
@@ -542,19 +583,24 @@ int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, floa
   }
 #undef FD_FWD
   if (rc) return rc;
-  return check_launch();
+  rc = check_launch();
+  if (rc) return rc;
+  return flag_enqueue_copy(h, st);
 }
 
-int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
-                          const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
-                          void* stream) {
-  if (!h || !x_dev || !wrap_mask) return fail(FD_ERR_INVALID, "null argument");
+namespace {
+
+// Reverse steps t = t_hi-1 .. t_lo; the k-th executed step takes its normals from noise_dev slice k, or (noise_dev
+// == nullptr, philox) from elements [offset + k * slice, +slice) of the library stream `seed`.
+int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise_dev, bool philox, uint64_t seed,
+              uint64_t offset, float* history_dev, const uint8_t* wrap_mask, cudaStream_t st) {
   if (h->batch == 0) return fail(FD_ERR_STATE, "fd_set_batch has not been called");
   if (t_lo < 0 || t_hi > h->d.timesteps || t_lo >= t_hi)
     return fail(FD_ERR_INVALID, "need 0 <= t_lo < t_hi <= %d (got %d, %d)", h->d.timesteps, t_lo, t_hi);
-  if (!noise_dev && !(t_hi == 1 && t_lo == 0)) return fail(FD_ERR_INVALID, "noise_dev is required for steps with t > 0");
-  cudaStream_t st = (cudaStream_t)stream;
-  FD_CUDA(cudaSetDevice(h->device));
+  if (!noise_dev && !philox && !(t_hi == 1 && t_lo == 0)) return fail(FD_ERR_INVALID, "noise_dev is required for steps with t > 0");
+  DevGuard guard(h->device);
+  int rc = flag_poll(h);
+  if (rc) return rc;
   const int Hd = h->d.hidden, F = h->d.n_features;
   uint32_t wrap_bits = 0;
   for (int f = 0; f < F; ++f) wrap_bits |= (wrap_mask[f] ? 1u : 0u) << f;
@@ -562,14 +608,14 @@ int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo
   for (int t = t_hi - 1, k = 0; t >= t_lo; --t, ++k) {
     const float* c = &h->coef[(size_t)t * 4];
     fd::StepCoef coef{c[0], c[1], c[2], c[3], t > 0 ? 1 : 0};
-    const float* z = noise_dev ? noise_dev + (size_t)k * slice : nullptr;
+    fd::StepNoise noise{noise_dev ? noise_dev + (size_t)k * slice : nullptr, (unsigned long long)seed,
+                        (unsigned long long)(offset + (uint64_t)k * slice)};
     float* hist = history_dev ? history_dev + (size_t)k * slice : nullptr;
     const float* temb = h->time_table + (size_t)t * Hd;
-    int rc;
-#define FD_STEP(V)                                                                           \
-  case V:                                                                                    \
-    rc = run_encoder<V>(h, x_dev, temb, 0, st);                                              \
-    if (!rc) launch_tail<V, true>(h, nullptr, x_dev, z, hist, coef, wrap_bits, st);          \
+#define FD_STEP(V)                                                                               \
+  case V:                                                                                        \
+    rc = run_encoder<V>(h, x_dev, temb, 0, st);                                                  \
+    if (!rc) launch_tail<V, true>(h, nullptr, x_dev, noise, hist, coef, wrap_bits, st);          \
     break;
     switch (Hd / 32) {
       FD_STEP(2) FD_STEP(4) FD_STEP(6) FD_STEP(8) FD_STEP(10) FD_STEP(12) FD_STEP(14) FD_STEP(16)
@@ -578,7 +624,29 @@ int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo
 #undef FD_STEP
     if (rc) return rc;
   }
-  return check_launch();
+  rc = check_launch();
+  if (rc) return rc;
+  return flag_enqueue_copy(h, st);
+}
+
+}  // namespace
+
+int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
+                          const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
+                          void* stream) {
+  if (!h || !x_dev || !wrap_mask) return fail(FD_ERR_INVALID, "null argument");
+  return run_steps(h, x_dev, t_hi, t_lo, noise_dev, false, 0, 0, history_dev, wrap_mask, (cudaStream_t)stream);
+}
+
+int32_t fd_p_sample_steps_philox(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo, uint64_t seed,
+                                 uint64_t offset, float* history_dev, const uint8_t* wrap_mask, void* stream) {
+  if (!h || !x_dev || !wrap_mask) return fail(FD_ERR_INVALID, "null argument");
+  return run_steps(h, x_dev, t_hi, t_lo, nullptr, true, seed, offset, history_dev, wrap_mask, (cudaStream_t)stream);
+}
+
+int32_t fd_status(fd_handle* h) {
+  if (!h) return fail(FD_ERR_INVALID, "null handle");
+  return flag_poll(h);
 }
 
 int32_t fd_randn(float* dst_dev, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
@@ -594,7 +662,7 @@ int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t
                        float* out_host) {
   if (!h || !lengths || !x0_host || !wrap_mask || !out_host) return fail(FD_ERR_INVALID, "null argument");
   if (t_start < 1 || t_start > h->d.timesteps) return fail(FD_ERR_INVALID, "t_start=%d", t_start);
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   cudaStream_t st;
   FD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   int rc = fd_set_batch(h, batch, n_pad, lengths, 0, nullptr, st);
@@ -603,7 +671,7 @@ int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t
   float *x = nullptr, *z = nullptr, *hist = nullptr;
   auto cleanup = [&]() { cudaFree(x); cudaFree(z); cudaFree(hist); cudaStreamDestroy(st); };
   if (!rc && cudaMalloc(&x, sizeof(float) * slice) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc x");
-  if (!rc && cudaMalloc(&z, sizeof(float) * slice * chunk) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc noise");
+  if (!rc && noise_host && cudaMalloc(&z, sizeof(float) * slice * chunk) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc noise");
   if (!rc && full_history && cudaMalloc(&hist, sizeof(float) * slice * chunk) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc history");
   if (!rc && cudaMemcpyAsync(x, x0_host, sizeof(float) * slice, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "H2D x0");
   if (!rc && hist) cudaMemsetAsync(hist, 0, sizeof(float) * slice * chunk, st);
@@ -614,10 +682,10 @@ int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t
     if (noise_host) {
       if (cudaMemcpyAsync(z, noise_host + (size_t)done * slice, sizeof(float) * slice * n, cudaMemcpyHostToDevice, st) != cudaSuccess)
         rc = fail(FD_ERR_CUDA, "H2D noise");
-    } else {
-      rc = fd_randn(z, (int64_t)(slice * n), seed, (uint64_t)done * slice, st);
+      if (!rc) rc = fd_p_sample_steps(h, x, t_hi, t_hi - n, z, hist, wrap_mask, st);
+    } else {  // the library's own stream: element (step, b, n, f) of `seed`, drawn inside the tail kernel
+      rc = fd_p_sample_steps_philox(h, x, t_hi, t_hi - n, seed, (uint64_t)done * slice, hist, wrap_mask, st);
     }
-    if (!rc) rc = fd_p_sample_steps(h, x, t_hi, t_hi - n, z, hist, wrap_mask, st);
     if (!rc && hist &&
         cudaMemcpyAsync(out_host + (size_t)done * slice, hist, sizeof(float) * slice * n, cudaMemcpyDeviceToHost, st) != cudaSuccess)
       rc = fail(FD_ERR_CUDA, "D2H history");
@@ -626,6 +694,7 @@ int32_t fd_sample_host(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t
   if (!rc && !full_history && cudaMemcpyAsync(out_host, x, sizeof(float) * slice, cudaMemcpyDeviceToHost, st) != cudaSuccess)
     rc = fail(FD_ERR_CUDA, "D2H result");
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "sample_host: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc) rc = flag_poll(h);  // a timed-out pipeline must not return garbage as a success
   cleanup();
   return rc;
 }
@@ -706,28 +775,23 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
     FD_CUDA(cudaMemcpyAsync(e_pad, dist_dev, sizeof(float) * 255 * FD_HEAD_DIM, cudaMemcpyDeviceToDevice, st));
     fd::tc_split_kernel<<<16, 256, 0, st>>>(e_pad, e_hi, e_lo, ne / 4, 1.0f);
     fd::tc_split_kernel<<<256, 256, 0, st>>>(qkv_dev, q_hi, q_lo, nq / 4, 1.0f);
-    cudaFuncSetAttribute(fd::attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
-    cudaFuncSetAttribute(fd::attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::att_smem_bytes());
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int items = batch * heads, want = (items + fd::ATT_GROUPS - 1) / fd::ATT_GROUPS, grid = want < sms ? want : sms;
+    const int items = batch * heads;
     if (fd::atc_enabled() && mode == FD_GEMM_TC_3X) {
       CUtensorMap m_hi, m_lo;
       int arc = fd::attp_make_map(&m_hi, q_hi, rows + 128, 3 * H) || fd::attp_make_map(&m_lo, q_lo, rows + 128, 3 * H);
       if (!arc) arc = fd::atc_launch(m_hi, m_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st);
       if (arc) rc = fail(FD_ERR_CUDA, "debug attention: tcgen05 launch failed (%d)", arc);
-    } else if (fd::attp_enabled()) {
+    } else {
       CUtensorMap m_hi, m_lo;
       int arc = fd::attp_make_map(&m_hi, q_hi, rows + 128, 3 * H) || fd::attp_make_map(&m_lo, q_lo, rows + 128, 3 * H);
       if (!arc) arc = mode == FD_GEMM_TC_3X
           ? fd::attp_launch<true>(m_hi, m_lo, q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st)
           : fd::attp_launch<false>(m_hi, m_lo, q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo, sms, st);
       if (arc) rc = fail(FD_ERR_CUDA, "debug attention: pool launch failed (%d)", arc);
-    } else if (mode == FD_GEMM_TC_3X)
-      fd::attention_mma_kernel<true><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
-    else
-      fd::attention_mma_kernel<false><<<grid, fd::ATT_WARPS * 32, fd::att_smem_bytes(), st>>>(q_hi, q_lo, d_rs, d_nr, d_nk, nullptr, n_pad, e_hi, e_lo, H, heads, items, c_hi, c_lo);
+    }
     fd_join_planes_kernel<<<256, 256, 0, st>>>(c_hi, mode == FD_GEMM_TC_3X ? c_lo : nullptr, ctx_out_dev, nc);
     cudaStreamSynchronize(st);
     cudaFree(q_hi); cudaFree(q_lo); cudaFree(c_hi); cudaFree(c_lo); cudaFree(e_hi); cudaFree(e_lo); cudaFree(e_pad);
@@ -739,7 +803,7 @@ int32_t fd_debug_attention(int32_t mode, const float* qkv_dev, int32_t batch, in
 
 int32_t fd_profile_begin(fd_handle* h) {
   if (!h) return fail(FD_ERR_INVALID, "null handle");
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   FD_CUDA(cudaDeviceSynchronize());
   h->prof_used = 0;
   h->prof_cat.clear();
@@ -750,7 +814,7 @@ int32_t fd_profile_begin(fd_handle* h) {
 int32_t fd_profile_end(fd_handle* h, float* ms_out, int64_t* launches_out) {
   if (!h || !ms_out || !launches_out) return fail(FD_ERR_INVALID, "null argument");
   h->prof_on = false;
-  FD_CUDA(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   FD_CUDA(cudaDeviceSynchronize());
   for (int c = 0; c < CAT_COUNT; ++c) { ms_out[c] = 0.0f; launches_out[c] = 0; }
   for (size_t i = 0; i < h->prof_cat.size(); ++i) {

@@ -4,12 +4,10 @@
 //   (transformers 4.11.3 BertSelfAttention, position_embedding_type = "relative_key";
 //    call site /root/reference/foldingdiff/modelling.py:473)
 //
-// Shapes are tiny (n <= 128 residues, head_dim 32), so the work item is one (chain, head): 8 warps x 16
-// query rows against all keys of the chain, which sit in shared memory.  The kernel is persistent
-// (one CTA per SM, 16 warps): the layer's distance-embedding table is staged ONCE per CTA, and the
-// CTA runs TWO independent 8-warp groups, each walking its own stream of work items - while one
-// group stages K / V of its next item, the other is in its math phase (ncu on the first version:
-// latency-bound at 8 warps / SM, dependent-MMA chains exposed).
+// Building blocks of the mma.sync attention kernel (attention_pool.cuh, used by the 1-pass tc1x mode and as the A/B
+// alternative of the tcgen05 kernel): one warp = 16 query rows of one (chain, head) against all keys of the chain,
+// which sit in shared memory.  (The first kernel built on them - two fixed 8-warp groups per CTA - was superseded by
+// the warp-pool kernel in round 1 and has been removed.)
 //
 //   * operands are the fp16 hi / lo planes the QKV GEMM epilogue wrote; every product runs as the
 //     error-compensated triple  hi*hi + hi*lo + lo*hi  (same scheme as gemm_tc.cuh), fp32 accumulate
@@ -30,20 +28,11 @@
 
 namespace fd {
 
-constexpr int ATT_GROUP_WARPS = 8;  // 8 warps x 16 query rows = the whole chain (n <= 128)
-constexpr int ATT_GROUPS = 2;       // independent warp groups per CTA
-constexpr int ATT_WARPS = ATT_GROUP_WARPS * ATT_GROUPS;
+constexpr int ATT_WARPS = 16;
 constexpr int ATT_PITCH = 32;     // halves per smem row: unpadded 64-byte rows, 16-byte chunks XOR-swizzled (att_sw)
 constexpr int ATT_RP = 56;        // fp32 scratch pitch (== 24 mod 32: conflict-free float2 stores; >= 32 + 16 columns)
 constexpr int ATT_E_TABLE = 256;  // rows of the padded per-layer table (255 real + 1 zero row)
 constexpr int ATT_KV_HALVES = 128 * ATT_PITCH;  // one K or V plane of one work item
-
-constexpr size_t att_smem_bytes() {
-  return (size_t)2 * ATT_E_TABLE * ATT_PITCH * 2      // E hi/lo, whole table, resident for the kernel's life
-         + (size_t)ATT_GROUPS * 2 * 4 * ATT_KV_HALVES * 2   // per group, double-buffered {K hi, K lo, V hi, V lo}
-         + (size_t)ATT_WARPS * 16 * ATT_RP * 4              // R scratch
-         + (size_t)ATT_GROUPS * 2 * 128 * 4;                // per group, double-buffered key bias
-}
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -88,36 +77,6 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// Stage K and V of one work item (chain, head) into a shared-memory buffer {K hi, K lo, V hi, V lo}.
-template <bool THREE>
-__device__ __forceinline__ void att_stage_kv(__half* buf, float* bias_s, const __half* __restrict__ qkv_hi,
-                                             const __half* __restrict__ qkv_lo, const float* __restrict__ key_bias,
-                                             int chain, int head, int r0, int n_keys, int n_pad, int H) {
-  const int gtid = threadIdx.x & (ATT_GROUP_WARPS * 32 - 1);  // thread index inside the warp group
-  const int nk16 = (n_keys + 15) & ~15, ld = 3 * H;
-  __half* Ks_hi = buf; __half* Ks_lo = buf + ATT_KV_HALVES;
-  __half* Vs_hi = buf + 2 * ATT_KV_HALVES; __half* Vs_lo = buf + 3 * ATT_KV_HALVES;
-  for (int i = gtid; i < nk16 * 4; i += ATT_GROUP_WARPS * 32) {
-    const int r = i >> 2, c = (i & 3) * 8;  // 8 halves = 16 bytes
-    const int so = att_sw(r, i & 3);
-    if (r < n_keys) {
-      const size_t off = (size_t)(r0 + r) * ld + head * FD_HEAD_DIM + c;
-      cp_async16(Ks_hi + so, qkv_hi + off + H);
-      cp_async16(Vs_hi + so, qkv_hi + off + 2 * H);
-      if (THREE) { cp_async16(Ks_lo + so, qkv_lo + off + H); cp_async16(Vs_lo + so, qkv_lo + off + 2 * H); }
-    } else {  // rows padding the key count up to a multiple of 16: zeros (P is 0 there, 0 * 0 = 0)
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(Ks_hi + so) = z; *reinterpret_cast<uint4*>(Vs_hi + so) = z;
-      if (THREE) { *reinterpret_cast<uint4*>(Ks_lo + so) = z; *reinterpret_cast<uint4*>(Vs_lo + so) = z; }
-    }
-  }
-  for (int i = gtid; i < nk16; i += ATT_GROUP_WARPS * 32)
-    bias_s[i] = (i < n_keys) ? (key_bias ? key_bias[(size_t)chain * n_pad + i] * 1.44269504088896340736f : 0.0f)
-                             : -INFINITY;  // pre-multiplied by log2(e): the softmax works in log2 units
-}
-
-// Q fragments (A operand of m16n8k16: 16 rows x 32 head dims) of one warp, straight from global.
-// Issued BEFORE the K / V staging of the item so the L2 latency hides behind the cp.async wait.
 template <bool THREE>
 __device__ __forceinline__ void att_load_q(uint32_t (&qa_hi)[2][4], uint32_t (&qa_lo)[2][4],
                                            const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
@@ -304,72 +263,6 @@ __device__ __forceinline__ void att_rows(const __half* kv, const __half* Es_hi, 
       if (THREE) *reinterpret_cast<uint32_t*>(ctx_lo + (size_t)(r0 + rb) * H + c) = lo;
     }
   }
-}
-
-__device__ __forceinline__ void att_group_barrier(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(ATT_GROUP_WARPS * 32) : "memory");
-}
-
-// Persistent kernel: grid <= #SMs; work item w = chain * heads + head.  Warp group `grp` of CTA `b` takes
-// items (b * 2 + grp), (b * 2 + grp) + 2 * grid, ...  The two groups only share the (read-only) distance
-// table; each has its own K / V buffer, bias row and named barrier.  THREE: 3-pass split or hi*hi only.
-template <bool THREE>
-__global__ void __launch_bounds__(ATT_WARPS * 32, 1)
-attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
-                     const int* __restrict__ row_start, const int* __restrict__ n_rows_arr,
-                     const int* __restrict__ n_keys_arr, const float* __restrict__ key_bias, int n_pad,
-                     const __half* __restrict__ e_hi, const __half* __restrict__ e_lo, int H, int heads,
-                     int n_items, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  __half* Es_hi = reinterpret_cast<__half*>(att_smem);
-  __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
-  __half* kv0 = Es_lo + ATT_E_TABLE * ATT_PITCH;       // group g, buffer b: kv0 + (g * 2 + b) * 4 * ATT_KV_HALVES
-  float* Rs = reinterpret_cast<float*>(kv0 + ATT_GROUPS * 2 * 4 * ATT_KV_HALVES);
-  float* Bs0 = Rs + ATT_WARPS * 16 * ATT_RP;           // group g, buffer b: Bs0 + (g * 2 + b) * 128
-
-  const int tid = threadIdx.x, warp = tid >> 5, grp = warp / ATT_GROUP_WARPS, gwarp = warp % ATT_GROUP_WARPS;
-  for (int i = tid; i < ATT_E_TABLE * 4; i += ATT_WARPS * 32) {
-    const int r = i >> 2;
-    cp_async16(Es_hi + att_sw(r, i & 3), e_hi + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
-    if (THREE) cp_async16(Es_lo + att_sw(r, i & 3), e_lo + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  __half* kvg = kv0 + grp * 2 * 4 * ATT_KV_HALVES;
-  float* Bsg = Bs0 + grp * 2 * 128;
-  float* Rw = Rs + warp * 16 * ATT_RP;
-  const int stride = gridDim.x * ATT_GROUPS;
-  int item = blockIdx.x * ATT_GROUPS + grp;
-  // item metadata is read one item ahead so its L2 latency never sits on the critical path
-  int chain = 0, head = 0, r0 = 0, n_rows = 0, n_keys = 0;
-  if (item < n_items) {
-    chain = item / heads; head = item % heads;
-    r0 = row_start[chain]; n_rows = n_rows_arr[chain]; n_keys = n_keys_arr[chain];
-    att_stage_kv<THREE>(kvg, Bsg, qkv_hi, qkv_lo, key_bias, chain, head, r0, n_keys, n_pad, H);
-  }
-  for (int it = 0; item < n_items; item += stride, ++it) {
-    const int buf = it & 1;
-    const int l0 = gwarp * 16;
-    uint32_t qa_hi[2][4], qa_lo[2][4];
-    if (l0 < n_rows) att_load_q<THREE>(qa_hi, qa_lo, qkv_hi, qkv_lo, r0, l0, n_rows, head, H);
-    const int nitem = item + stride;
-    int nchain = 0, nhead = 0, nr0 = 0, nn_rows = 0, nn_keys = 0;
-    if (nitem < n_items) {
-      nchain = nitem / heads; nhead = nitem % heads;
-      nr0 = row_start[nchain]; nn_rows = n_rows_arr[nchain]; nn_keys = n_keys_arr[nchain];
-    }
-    cp_async_wait_all();
-    att_group_barrier(grp);  // this item's K / V / bias are visible; everyone has left the other buffer
-    if (nitem < n_items)     // stage the next item under this item's math
-      att_stage_kv<THREE>(kvg + (buf ^ 1) * 4 * ATT_KV_HALVES, Bsg + (buf ^ 1) * 128, qkv_hi, qkv_lo, key_bias, nchain,
-                          nhead, nr0, nn_keys, n_pad, H);
-    if (l0 < n_rows)
-      att_rows<THREE>(kvg + buf * 4 * ATT_KV_HALVES, Es_hi, Es_lo, Rw, Bsg + buf * 128, qa_hi, qa_lo, r0, l0, n_rows,
-                      n_keys, head, H, ctx_hi, ctx_lo);
-    chain = nchain; head = nhead; r0 = nr0; n_rows = nn_rows; n_keys = nn_keys;
-  }
-  cp_async_wait_all();
 }
 
 }  // namespace fd

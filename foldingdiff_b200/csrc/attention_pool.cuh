@@ -205,16 +205,6 @@ inline int attp_make_map(CUtensorMap* map, const __half* base, int rows, int ld)
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-// FOLDINGDIFF_B200_ATT=groups selects the older fixed-group kernel (attention_mma.cuh) for A/B runs.
-inline bool attp_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("FOLDINGDIFF_B200_ATT");
-    on = (e && e[0] == 'g') ? 0 : 1;
-  }
-  return on == 1;
-}
-
 template <bool THREE>
 inline int attp_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const __half* qkv_hi, const __half* qkv_lo,
                        const int* row_start, const int* n_rows, const int* n_keys, const float* key_bias, int n_pad,

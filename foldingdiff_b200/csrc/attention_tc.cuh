@@ -103,6 +103,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+// split2 (attention_mma.cuh) of (x0, x1) * (1 + c), c ~ 1e-6, with the scale folded into the lo words:
+// hi = fp16(x), lo = fp16(x - hi * t), t = 1 - c  (= (x - hi) + hi * c; below 1 the fp32 grid is twice as fine as above)
+__device__ __forceinline__ void split2s(float x0, float x1, float t, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(fmaf(-hf.x, t, x0), fmaf(-hf.y, t, x1));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // mbarrier helpers on shared-space addresses (computed once per thread).  The wait passes a suspend-time hint:
@@ -165,7 +174,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     const int* __restrict__ n_keys_arr, const float* __restrict__ key_bias, int n_pad,
                     const __half* __restrict__ e_hi, const __half* __restrict__ e_lo, int H, int heads, int n_items,
                     __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo, AtcDesc dsc, float* __restrict__ dbg,
-                    int* __restrict__ err_flag) {
+                    int* __restrict__ err_flag, float rz_alpha, float rz_beta) {
+  pdl_trigger();
   extern __shared__ uint8_t atc_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
@@ -220,6 +230,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // the prologue (barriers, TMEM, the layer's distance table: weights) ran under the QKV GEMM's tail
   // shared-space addresses of the barriers (8 bytes each, same order as above)
   const uint32_t b_kv_full = smem_u32(kv_full), b_kv_empty = smem_u32(kv_empty), b_sr_full = smem_u32(sr_full);
   const uint32_t b_o_full = smem_u32(o_full), b_sr_empty = smem_u32(sr_empty), b_o_empty = smem_u32(o_empty);
@@ -471,9 +482,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
           for (int g = 0; g < 2; ++g) {  // 32 keys -> 16 packed columns per plane
             if (64 * r + 32 * g < nk32) {
               uint32_t ph[16], pl[16];
+              // accumulation de-bias of O = P V (gemm_tc.cuh: tc_rz): the 16-key chunk j of nk32 / 16 still has
+              // 3 (nk32 / 16 - j) truncating accumulates ahead of it; its inverse rides in the lo plane for free
+              // (lo = p - hi * (1 - c) is the FSUB of the plain split turned into an FMA)
+              const float sc0 = 1.0f - (rz_alpha + rz_beta * (float)((nk32 >> 4) - (4 * r + 2 * g)));
+              const float sc1 = 1.0f - (rz_alpha + rz_beta * (float)((nk32 >> 4) - (4 * r + 2 * g + 1)));
 #pragma unroll
               for (int q = 0; q < 16; ++q)
-                split2(__uint_as_float(su[64 * r + 32 * g + 2 * q]), __uint_as_float(su[64 * r + 32 * g + 2 * q + 1]), ph[q], pl[q]);
+                split2s(__uint_as_float(su[64 * r + 32 * g + 2 * q]), __uint_as_float(su[64 * r + 32 * g + 2 * q + 1]),
+                        q < 8 ? sc0 : sc1, ph[q], pl[q]);
               tmem_st16(t_lane + ATC_COL_P + 16 * g, ph);
               tmem_st16(t_lane + ATC_COL_P + 32 + 16 * g, pl);
             }
@@ -522,418 +539,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Version 2: TWO threads per query row.
-//
-// ncu on the kernel above (profiles/r01_attention_tc_ncu.md): correct, tensor pipe 19%, but latency-bound - its 8
-// softmax warps (2 per scheduler) each walk a ~1500-instruction dependent chain per item at ~0.1 IPC.  Here a row
-// is shared by two threads of two different warps (same TMEM lane quadrant, key halves [0,64) and [64,128)), so
-// 16 softmax warps (4 per scheduler) each do half the serial work: S / R loads, skew, mask, exp and the P write
-// are split by keys (key half h is exactly P round h), the output columns by dims (16 each); the row max and the
-// row sum cross the pair through shared memory and a 256-thread named barrier.  The ring is split into a Q/K ring
-// (2 slots, released when the S / R products retire) and a V ring (3 slots, released when P V retires) to pay for
-// the second warpgroup's skew scratch.  TMEM layout, barrier protocol and MMA issue order are those of version 1.
-constexpr int ATC2_THREADS = 640;  // warpgroups 0..3 = softmax (pairs {0,1} and {2,3}), warpgroup 4 = producers
-constexpr int ATC2_QK_SLOTS = 2, ATC2_V_SLOTS = 3;
-constexpr int ATC2_QK_BYTES = 4 * ATC_PLANE_BYTES, ATC2_V_BYTES = 2 * ATC_PLANE_BYTES;
-constexpr size_t atc2_smem_bytes() {
-  return (size_t)ATC2_QK_SLOTS * ATC2_QK_BYTES + (size_t)ATC2_V_SLOTS * ATC2_V_BYTES + 2 * ATT_E_TABLE * 64
-         + (size_t)256 * ATC_SCR_PITCH * 4   // skew scratch: one thread-private row per thread of a pair
-         + 2 * 2 * 2 * 128 * 2 * 4           // row max / row sum exchange, per pair, double buffered
-         + 256 + 1024;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void atc_pair_sync(int pair) {
-  asm volatile("bar.sync %0, 256;" ::"r"(pair + 1) : "memory");
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 #undef ATC_ACTIVE
 
-template <bool DBG>
-__global__ void __launch_bounds__(ATC2_THREADS, 1)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                     const int* __restrict__ row_start, const int* __restrict__ n_rows_arr,
-                     const int* __restrict__ n_keys_arr, const float* __restrict__ key_bias, int n_pad,
-                     const __half* __restrict__ e_hi, const __half* __restrict__ e_lo, int H, int heads, int n_items,
-                     __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo, AtcDesc dsc, float* __restrict__ dbg,
-                     int* __restrict__ err_flag) {
-  extern __shared__ uint8_t atc_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* qk_ring = smem;
-  uint8_t* v_ring = smem + ATC2_QK_SLOTS * ATC2_QK_BYTES;
-  __half* Es_hi = reinterpret_cast<__half*>(v_ring + ATC2_V_SLOTS * ATC2_V_BYTES);
-  __half* Es_lo = Es_hi + ATT_E_TABLE * ATT_PITCH;
-  float* scr = reinterpret_cast<float*>(Es_lo + ATT_E_TABLE * ATT_PITCH);
-  float* xch = scr + 256 * ATC_SCR_PITCH;  // [pair][max | sum][buffer][row][half]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 2 * 128 * 2);
-  uint64_t* qk_full = bars;            // [2] TMA -> MMA
-  uint64_t* qk_empty = bars + 2;       // [2] MMA -> TMA (S / R products retired)
-  uint64_t* v_full = bars + 4;         // [3] TMA -> MMA
-  uint64_t* v_empty = bars + 7;        // [3] MMA -> TMA (P V retired)
-  uint64_t* sr_full = bars + 10;       // [2] MMA -> softmax pair (it & 1)
-  uint64_t* o_full = bars + 12;        // [2] MMA -> softmax pair (it & 1)
-  uint64_t* s_empty = bars + 14;       // softmax -> MMA, 8 warps
-  uint64_t* sr_empty = bars + 15;      // softmax -> MMA, 8 warps
-  uint64_t* o_empty = bars + 16;       // [2] softmax pair -> MMA, 8 warps (O is double buffered, one per pair)
-  uint64_t* p_full = bars + 18;        // [2] softmax half h -> MMA, 4 warps
-  uint64_t* p_empty = bars + 20;       // [2] MMA -> softmax
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qk_full[i], 1); mbar_init(&qk_empty[i], 1); mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1);
-      mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
-    }
-    for (int i = 0; i < 3; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    mbar_init(s_empty, 8); mbar_init(sr_empty, 8); mbar_init(&o_empty[0], 8); mbar_init(&o_empty[1], 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
-  }
-  if (warp == 17) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < ATT_E_TABLE * 4; i += ATC2_THREADS) {
-    const int r = i >> 2;
-    cp_async16(Es_hi + att_sw(r, i & 3), e_hi + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
-    cp_async16(Es_lo + att_sw(r, i & 3), e_lo + (size_t)r * FD_HEAD_DIM + (i & 3) * 8);
-  }
-  cp_async_wait_all();
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t b_qk_full = smem_u32(qk_full), b_qk_empty = smem_u32(qk_empty), b_v_full = smem_u32(v_full);
-  const uint32_t b_v_empty = smem_u32(v_empty), b_sr_full = smem_u32(sr_full), b_o_full = smem_u32(o_full);
-  const uint32_t b_s_empty = smem_u32(s_empty), b_sr_empty = smem_u32(sr_empty), b_o_empty = smem_u32(o_empty);
-  const uint32_t b_p_full = smem_u32(p_full), b_p_empty = smem_u32(p_empty);
-
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    if (warp == 16) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
-        for (int it = 0; it < n_it; ++it) {
-          const int qs = it % ATC2_QK_SLOTS, vs = it % ATC2_V_SLOTS;
-          const AtcItem a = nxt;
-          nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-          const int cq = a.head * FD_HEAD_DIM;
-          if (!atc_wait(b_qk_empty + 8 * qs, (uint32_t)(((it / ATC2_QK_SLOTS) & 1) ^ 1))) { atomicExch(err_flag, 401); break; }
-          uint8_t* s = qk_ring + (size_t)qs * ATC2_QK_BYTES;
-          mbar_expect_tx(&qk_full[qs], ATC2_QK_BYTES);
-          tma_load_2d(s, &map_hi, &qk_full[qs], cq, a.r0);
-          tma_load_2d(s + 2 * ATC_PLANE_BYTES, &map_hi, &qk_full[qs], H + cq, a.r0);
-          tma_load_2d(s + 1 * ATC_PLANE_BYTES, &map_lo, &qk_full[qs], cq, a.r0);
-          tma_load_2d(s + 3 * ATC_PLANE_BYTES, &map_lo, &qk_full[qs], H + cq, a.r0);
-          if (!atc_wait(b_v_empty + 8 * vs, (uint32_t)(((it / ATC2_V_SLOTS) & 1) ^ 1))) { atomicExch(err_flag, 402); break; }
-          uint8_t* v = v_ring + (size_t)vs * ATC2_V_BYTES;
-          mbar_expect_tx(&v_full[vs], ATC2_V_BYTES);
-          tma_load_2d(v, &map_hi, &v_full[vs], 2 * H + cq, a.r0);
-          tma_load_2d(v + ATC_PLANE_BYTES, &map_lo, &v_full[vs], 2 * H + cq, a.r0);
-        }
-      }
-    } else if (warp == 17) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
-        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
-        for (int it = 0; it < n_it; ++it) {
-          {  // ---- S and R of item `it`
-            const AtcItem a = nxt;
-            nxt = atc_item(min(it + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-            const int nk32 = a.nk32(), nr32 = a.nr32();
-            const int qs = it % ATC2_QK_SLOTS;
-            if (!atc_wait(b_qk_full + 8 * qs, (uint32_t)((it / ATC2_QK_SLOTS) & 1))) { atomicExch(err_flag, 403); break; }
-            if (!atc_wait(b_s_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 404); break; }
-            tc_fence_after();
-            const uint32_t s0 = smem_u32(qk_ring + (size_t)qs * ATC2_QK_BYTES);
-            const uint32_t q_hi = s0, q_lo = s0 + ATC_PLANE_BYTES, k_hi = s0 + 2 * ATC_PLANE_BYTES, k_lo = s0 + 3 * ATC_PLANE_BYTES;
-            const uint32_t id_s = umma_idesc_f16(nk32), id_r = umma_idesc_f16(nk32 + nr32);
-            const uint32_t e_off = (uint32_t)(128 - nk32) * 64u;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t ko = ks * 32;
-              const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
-              umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, ks);
-              umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_lo + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
-              umma_f16(tmem + ATC_COL_S, dq_lo, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
-            }
-            if (!atc_wait(b_sr_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 405); break; }
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t ko = ks * 32;
-              const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
-              umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, ks);
-              umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_lo_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
-              umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
-            }
-            atc_commit(b_sr_full + 8 * (it & 1));
-            atc_commit(b_qk_empty + 8 * qs);
-          }
-        }
-      }
-    } else if (warp == 18) {
-      // ===================== MMA issuer 2: O = P V (own thread, see version 1) =====================
-      if (lane == 0) {
-        bool ok = true;
-        AtcItem nxt = atc_item(0, n_items, heads, row_start, n_rows_arr, n_keys_arr);
-        for (int j = 0; j < n_it && ok; ++j) {
-          {  // ---- O = P V of item j, round r = key half r
-            const int vs = j % ATC2_V_SLOTS;
-            const AtcItem a = nxt;
-            nxt = atc_item(min(j + 1, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-            const int nk32 = a.nk32();
-            const uint32_t s0 = smem_u32(v_ring + (size_t)vs * ATC2_V_BYTES);
-            const uint32_t v_hi = s0, v_lo = s0 + ATC_PLANE_BYTES;
-            if (!atc_wait(b_v_full + 8 * vs, (uint32_t)((j / ATC2_V_SLOTS) & 1))) { atomicExch(err_flag, 406); break; }
-            if (!atc_wait(b_o_empty + 8 * (j & 1), (uint32_t)(((j >> 1) & 1) ^ 1))) { atomicExch(err_flag, 407); break; }
-            const uint32_t t_o = tmem + ATC_COL_O + 32 * (j & 1);
-            for (int r = 0; r < 2 && ok; ++r) {
-              if (!atc_wait(b_p_full + 8 * r, (uint32_t)(j & 1))) { atomicExch(err_flag, 408); ok = false; break; }
-              tc_fence_after();
-              const int nks = min(4, (nk32 - 64 * r) >> 4);
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint32_t vb = (uint32_t)(64 * r + 16 * ks) * 64u;
-                const uint32_t p_hi = tmem + ATC_COL_P + 8 * ks, p_lo = tmem + ATC_COL_P + 32 + 8 * ks;
-                umma_f16_ts(t_o, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
-                umma_f16_ts(t_o, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
-                umma_f16_ts(t_o, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
-              }
-              atc_commit(b_p_empty + 8 * r);
-            }
-            atc_commit(b_o_full + 8 * (j & 1));
-            atc_commit(b_v_empty + 8 * vs);
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== softmax warps: pair = item parity, half = key half, quad = TMEM lane quadrant =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    const int wgi = warp >> 2, pair = wgi >> 1, half = wgi & 1, quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t srow_s = smem_u32(scr + (size_t)(half * 128 + row) * ATC_SCR_PITCH), win_s = srow_s + 4u * (uint32_t)(lane + 31);
-    const uint32_t xm_s = smem_u32(xch + (size_t)(pair * 2 + 0) * 512 + row * 2);  // [buffer][row][half] row max
-    const uint32_t xs_s = smem_u32(xch + (size_t)(pair * 2 + 1) * 512 + row * 2);  // [buffer][row][half] row sum
-    // The output of an item is finished one iteration LATER (under the next item's P V hand-off): O is double
-    // buffered in TMEM (one buffer per pair), and the row sums cross the pair through the max-exchange barrier of
-    // the next item - so an item costs one named barrier and no wait for its own P V.
-    AtcItem pa = {0, 0, 0, 0, 0};
-    bool have_prev = false;
-    auto finish = [&](const AtcItem& q, uint32_t qpar, uint32_t xbuf) -> bool {  // epilogue of this pair's item q
-      if (!atc_wait(b_o_full + 8 * pair, qpar)) { if (lane == 0) atomicExch(err_flag, 412); return false; }
-      tc_fence_after();
-      const bool q_active = quad * 32 < q.n_rows;
-      uint32_t o[16];
-      if (q_active) tmem_ld16(t_lane + ATC_COL_O + 32 * pair + 16 * half, o);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_o_empty + 8 * pair);
-      if (q_active && row < q.n_rows) {
-        const float tot = lds_f32(xs_s + 1024 * xbuf) + lds_f32(xs_s + 1024 * xbuf + 4);
-        const float inv = 1.0f / tot;
-        if (DBG && dbg) {
-          float* qrow = dbg + ((size_t)(q.chain * heads + q.head) * 128 + row) * ATC_DBG_ROW;
-#pragma unroll
-          for (int d = 0; d < 16; ++d) qrow[256 + 16 * half + d] = __uint_as_float(o[d]);
-          if (half == 0) qrow[289] = tot;
-        }
-        uint32_t oh[8], ol[8];
-#pragma unroll
-        for (int q2 = 0; q2 < 8; ++q2)
-          split2(__uint_as_float(o[2 * q2]) * inv, __uint_as_float(o[2 * q2 + 1]) * inv, oh[q2], ol[q2]);
-        const size_t off = (size_t)(q.r0 + row) * H + q.head * FD_HEAD_DIM + 16 * half;
-#pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
-          *reinterpret_cast<uint4*>(ctx_hi + off + 8 * q2) = make_uint4(oh[4 * q2], oh[4 * q2 + 1], oh[4 * q2 + 2], oh[4 * q2 + 3]);
-          *reinterpret_cast<uint4*>(ctx_lo + off + 8 * q2) = make_uint4(ol[4 * q2], ol[4 * q2 + 1], ol[4 * q2 + 2], ol[4 * q2 + 3]);
-        }
-      }
-      return true;
-    };
-    const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
-    AtcItem nxt = atc_item(min(pair, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);
-    for (int it = pair; it < n_it; it += 2) {
-      const AtcItem a = nxt;
-      nxt = atc_item(min(it + 2, n_it - 1), n_items, heads, row_start, n_rows_arr, n_keys_arr);  // in flight under this item
-      const int nk32 = a.nk32();
-      const bool active = quad * 32 < a.n_rows;          // this warp's rows exist
-      const bool kact = active && 64 * half < nk32;      // ... and its key half is not empty
-      const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // wpar also picks the exchange buffer
-      float* drow = (DBG && dbg) ? dbg + ((size_t)(a.chain * heads + a.head) * 128 + row) * ATC_DBG_ROW : nullptr;
-      uint32_t su[64];
-      if (!atc_wait(b_sr_full + 8 * pair, wpar)) { if (lane == 0) atomicExch(err_flag, 409); break; }
-      tc_fence_after();
-      if (kact) {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-          if (64 * half + 32 * cc < nk32)
-            tmem_ld32_issue(t_lane + ATC_COL_S + 64 * half + 32 * cc, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * cc]));
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_s_empty);
-      if (kact) {
-        if (DBG && drow) {
-#pragma unroll
-          for (int k = 0; k < 64; ++k) if (64 * half + k < nk32) drow[64 * half + k] = __uint_as_float(su[k]);
-        }
-        // ---- skew: S[l, 32 c + i] += R[l, 32 (quad - c) + nk32 - 32 + (lane - i + 31)],  c = 2 half + cc
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (64 * half + 32 * cc < nk32) {
-            const uint32_t cb = (uint32_t)(32 * (quad - 2 * half - cc) + nk32 - 32);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint32_t v[16];
-              tmem_ld16(t_lane + ATC_COL_R + cb + 16 * q4, v);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) sts_v4(srow_s + 64 * q4 + 16 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              su[32 * cc + i] = __float_as_uint(__uint_as_float(su[32 * cc + i]) + lds_f32(win_s - 4u * (uint32_t)i));
-          }
-        }
-        if (DBG && drow) {
-#pragma unroll
-          for (int k = 0; k < 64; ++k) if (64 * half + k < nk32) drow[128 + 64 * half + k] = __uint_as_float(su[k]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_sr_empty);
-
-      // ---- mask, max of this key half, exchange, exp, sum of this key half
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      if (kact) {
-        if (key_bias) {
-          const float* kb = key_bias + (size_t)a.chain * n_pad;
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            if (64 * half + 32 * cc < nk32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int k = 64 * half + 32 * cc + i;
-                su[32 * cc + i] = __float_as_uint(fmaf(kb[min(k, a.n_keys - 1)], 5.65685424949238019521f, __uint_as_float(su[32 * cc + i])));
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int k0 = 64 * half + 32 * cc;
-          if (k0 < nk32) {
-            if (k0 + 32 > a.n_keys) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) su[32 * cc + i] = (k0 + i < a.n_keys) ? su[32 * cc + i] : 0xff800000u;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              m0 = fmaxf(m0, __uint_as_float(su[32 * cc + i])); m1 = fmaxf(m1, __uint_as_float(su[32 * cc + i + 1]));
-              m2 = fmaxf(m2, __uint_as_float(su[32 * cc + i + 2])); m3 = fmaxf(m3, __uint_as_float(su[32 * cc + i + 3]));
-            }
-          }
-        }
-      }
-      sts_f32(xm_s + 1024 * wpar + 4 * half, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      atc_pair_sync(pair);  // the pair's maxima of this item - and its sums of the previous one - are visible
-      const float m = fmaxf(lds_f32(xm_s + 1024 * wpar), lds_f32(xm_s + 1024 * wpar + 4));
-      float sum = 0.0f;
-      if (kact) {
-        const float neg = -m * c_scale;
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (64 * half + 32 * cc < nk32) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int k = 32 * cc + i;
-              const float p0 = ex2_approx(fmaf(__uint_as_float(su[k]), c_scale, neg));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(su[k + 1]), c_scale, neg));
-              const float p2 = ex2_approx(fmaf(__uint_as_float(su[k + 2]), c_scale, neg));
-              const float p3 = ex2_approx(fmaf(__uint_as_float(su[k + 3]), c_scale, neg));
-              su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
-              su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
-              s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-            }
-          }
-        }
-        sum = (s0 + s1) + (s2 + s3);
-      }
-      sts_f32(xs_s + 1024 * wpar + 4 * half, sum);  // read by finish() of this item, after the NEXT item's pair sync
-      if (DBG && drow && half == 0) drow[288] = m * c_scale;
-      // ---- P round `half`.  Both halves first wait for the previous item's round 1 to retire (exact by parity:
-      // this pair's own o_full of item it - 2 came after it), then half 1 for this item's round 0 (commit order).
-      if (!atc_wait(b_p_empty + 8, par ^ 1u)) { if (lane == 0) atomicExch(err_flag, 410); break; }
-      if (half == 1) {  // half 1 finishes the previous item while round 0 of this one goes through the tensor core
-        if (have_prev && !finish(pa, wpar ^ 1u, wpar ^ 1u)) break;
-        if (!atc_wait(b_p_empty, par)) { if (lane == 0) atomicExch(err_flag, 411); break; }
-      }
-      tc_fence_after();
-      if (kact) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (64 * half + 32 * g < nk32) {
-            uint32_t ph[16], pl[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              split2(__uint_as_float(su[32 * g + 2 * q]), __uint_as_float(su[32 * g + 2 * q + 1]), ph[q], pl[q]);
-            tmem_st16(t_lane + ATC_COL_P + 16 * g, ph);
-            tmem_st16(t_lane + ATC_COL_P + 32 + 16 * g, pl);
-          }
-        }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_p_full + 8 * half);
-      if (half == 0 && have_prev && !finish(pa, wpar ^ 1u, wpar ^ 1u)) break;
-      pa = a; have_prev = true;
-    }
-    if (have_prev) {  // the pair's last item: its sums need one more pair barrier
-      atc_pair_sync(pair);
-      const int last = pair + ((n_it - 1 - pair) & ~1);
-      finish(pa, (uint32_t)((last >> 1) & 1), (uint32_t)((last >> 1) & 1));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// FOLDINGDIFF_B200_ATT: unset / "tc" = version 1 (default: the fastest measured), "tc2" = version 2, "pool" =
-// attention_pool.cuh, "groups" = attention_mma.cuh.
-inline int atc_version() {  // 1: one thread per row (default), 2: two threads per row ("tc2"), 0: an mma.sync kernel
+// FOLDINGDIFF_B200_ATT: unset / "tc" = this kernel, "pool" = the mma.sync kernel of attention_pool.cuh.  (A second
+// tcgen05 version with two threads per query row was measured slower in round 1 - profiles/r01_attention_tc_analysis.md -
+// and has been removed.)
+inline bool atc_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FOLDINGDIFF_B200_ATT");
-    if (!e || !e[0] || (e[0] == 't' && e[1] == 'c' && e[2] != '2')) v = 1;
-    else if (e[0] == 't') v = 2;
-    else v = 0;  // "pool", "groups"
+    v = (!e || !e[0] || e[0] == 't') ? 1 : 0;
   }
-  return v;
+  return v != 0;
 }
-inline bool atc_enabled() { return atc_version() != 0; }
 inline float*& atc_debug_dump() {  // test hook: device buffer [items][128][ATC_DBG_ROW] or nullptr
   static float* p = nullptr;
   return p;
@@ -951,31 +569,17 @@ inline int atc_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, cons
   int* err = tc_err_flag();
   if (!err) return 11;
   const int grid = n_items < sm_count ? n_items : sm_count;
-  if (atc_version() == 2) {
-    static unsigned long long configured2 = 0;
-    if (tc_need_configure(&configured2) &&
-        (cudaFuncSetAttribute(attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc2_smem_bytes()) != cudaSuccess ||
-         cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc2_smem_bytes()) != cudaSuccess))
-      return 13;
-    if (atc_debug_dump())
-      attention_tc2_kernel<true><<<grid, ATC2_THREADS, atc2_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
-                                                                                n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
-                                                                                dsc, atc_debug_dump(), err);
-    else
-      attention_tc2_kernel<false><<<grid, ATC2_THREADS, atc2_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
-                                                                                 n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
-                                                                                 dsc, nullptr, err);
-    return cudaGetLastError() == cudaSuccess ? 0 : 12;
-  }
+  const TcRz rz = tc_rz();
+  cudaError_t e;
   if (atc_debug_dump())
-    attention_tc_kernel<true><<<grid, ATC_THREADS, atc_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
-                                                                           n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
-                                                                           dsc, atc_debug_dump(), err);
+    e = launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATC_THREADS), atc_smem_bytes(), st, map_hi, map_lo, row_start,
+                   n_rows, n_keys, key_bias, n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo, dsc, atc_debug_dump(), err,
+                   (float)rz.alpha, (float)rz.beta_att);
   else
-    attention_tc_kernel<false><<<grid, ATC_THREADS, atc_smem_bytes(), st>>>(map_hi, map_lo, row_start, n_rows, n_keys, key_bias,
-                                                                            n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo,
-                                                                            dsc, nullptr, err);
-  return cudaGetLastError() == cudaSuccess ? 0 : 12;
+    e = launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(ATC_THREADS), atc_smem_bytes(), st, map_hi, map_lo, row_start,
+                   n_rows, n_keys, key_bias, n_pad, e_hi, e_lo, H, heads, n_items, ctx_hi, ctx_lo, dsc, (float*)nullptr, err,
+                   (float)rz.alpha, (float)rz.beta_att);
+  return e == cudaSuccess ? 0 : 12;
 }
 
 }  // namespace fd

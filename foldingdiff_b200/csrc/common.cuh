@@ -3,11 +3,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #define FD_HEAD_DIM 32
 #define FD_MAX_FEATURES 16
 #define FD_ROW_TILE 256  // packed-row count is padded to this (two MMA M tiles: one per CTA of a 2-cluster)
 
 namespace fd {
+
+// Programmatic dependent launch (PDL).  Every kernel of the reverse step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below): kernel N + 1 may be scheduled onto SMs that
+// kernel N has already left and run its prologue (barrier init, TMEM allocation, tensor-map prefetch, the attention
+// kernel's distance-table load) under N's tail.  Contract kept by EVERY kernel on the step path:
+//   pdl_trigger()  first statement: the dependent grid may launch as soon as all CTAs of this one have started;
+//   pdl_wait()     before the first access (read OR write) to memory another kernel of the chain touches: returns
+//                  when the preceding grid has completed and its writes are visible.  Each kernel waits for its
+//                  predecessor, so completion is transitive along the chain (WAR hazards included).
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -60,5 +74,23 @@ __device__ __forceinline__ float wrap_pi(float v) {
   if (m != 0.0f && m < 0.0f) m = __fadd_rn(m, span);
   return __fadd_rn(m, lo);
 }
+
+// Host side: launch `kern` with the PDL attribute (FOLDINGDIFF_B200_PDL=0 turns the overlap off for A/B runs).
+#ifdef __CUDACC__
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FOLDINGDIFF_B200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace fd

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels_simt.cuh"  // EPI_* and gelu_erf
@@ -269,6 +270,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                float out_scale, int* __restrict__ err_flag, unsigned long long a_policy) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
   using Cfg = TcCfg<BN, NPASS, PAIR>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -306,6 +308,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; A planes / C are the chain's data
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -515,6 +518,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                   int* __restrict__ err_flag) {
   using Cfg = TcLnCfg<NH, NPASS>;
   constexpr int N = NH * 192;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -547,6 +551,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -770,6 +775,37 @@ __global__ void tc_absmax_kernel(const float* __restrict__ src, size_t n, unsign
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
 }
 
+// Accumulation de-bias (see tc_rz() below).  A weight matrix [n, k] is split into its fp16 hi / lo planes AFTER
+// every 16-column chunk c of K has been scaled by  1 + alpha + beta * (k/16 - c): the tensor core's fp32
+// accumulator truncates (round toward zero) at every tcgen05.mma, so the contribution of the chunk issued at
+// accumulate step s of S shrinks by ~ eps * (S - s + 1); the shrink is a linear functional of the per-chunk
+// products and the (static) weight operand can carry its inverse.  Rows < q_rows (the query rows of the fused QKV
+// weight) additionally carry the same correction for the two 16-wide chunks of the attention kernel's K = 32
+// products Q K^T and Q E^T (head dim d: chunk d / 16 of 2).  Create-time only: plain fp64 arithmetic.
+__global__ void tc_split_weight_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
+                                       int n, int k, double scale, double alpha, double beta, double beta_att, int q_rows) {
+  const size_t total = (size_t)n * k;
+  const int nk = k / 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / k), col = (int)(i % k);
+    double c = 1.0 + alpha + beta * (double)(nk - col / 16);
+    if (row < q_rows) c *= 1.0 + alpha + beta_att * (double)(2 - (row % FD_HEAD_DIM) / 16);
+    const double x = (double)src[i] * scale * c;
+    const __half h = __double2half(x);
+    hi[i] = h;
+    lo[i] = __double2half(x - (double)__half2float(h));
+  }
+}
+// bias of the query rows, scaled like those rows
+__global__ void tc_scale_qbias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int q_rows,
+                                      double alpha, double beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double c = 1.0;
+  if (i < q_rows) c = 1.0 + alpha + beta * (double)(2 - (i % FD_HEAD_DIM) / 16);
+  dst[i] = (float)((double)src[i] * c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -836,8 +872,36 @@ inline void tc_free_acts(TcActs* a) {
   tc_free_plane(&a->h); tc_free_plane(&a->qkv); tc_free_plane(&a->ctx); tc_free_plane(&a->a); tc_free_plane(&a->inter);
 }
 
+// Tensor-core accumulation de-bias constants (tc_split_weight_kernel; attention P split).
+// tools/rz_calib.py (B200, profiles/r02_rz_calibration.md): with same-sign operands a 16-wide K chunk of the 3-pass
+// product loses 2.8e-7 of the running sum per chunk still to come (alignment truncation of every product plus the
+// truncation of the sum); with zero-mean products - the network's case - only the part that is a linear functional
+// of the partial sums survives on average, ~1e-7 per chunk, and that is what a static pre-scale can cancel.
+// tools/rz_sweep.py then picked beta on the real network: forward error against the fp64 oracle (production shape)
+// rms 1.03e-6 at beta = 0 -> 2.38e-7 at beta = 0.975e-7, the fp32 CUDA-core path's own 2.37e-7.
+// FOLDINGDIFF_B200_RZ="alpha,beta[,beta_attention]" overrides ("0,0" = off).
+struct TcRz { double alpha, beta, beta_att; };
+inline TcRz tc_rz() {
+  static TcRz rz = [] {
+    TcRz r{0.0, 0.975e-7, 0.975e-7};
+    const char* e = getenv("FOLDINGDIFF_B200_RZ");
+    if (e && e[0]) {
+      char* end = nullptr;
+      const double a = strtod(e, &end);
+      if (end && *end == ',') {
+        r.alpha = a;
+        r.beta = r.beta_att = strtod(end + 1, &end);
+        if (end && *end == ',') r.beta_att = strtod(end + 1, nullptr);
+      }
+    }
+    return r;
+  }();
+  return rz;
+}
+
 // fp32 [n, k] device weight -> scaled fp16 hi / lo planes + TMA maps.  Synchronous (create time).
-inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out) {
+// q_rows: leading rows that are attention queries (fused QKV weight), see tc_split_weight_kernel.
+inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out, int q_rows = 0) {
   out->n = n; out->k = k; out->bn = tc_pick_bn(n);
   const size_t cnt = (size_t)n * k;
   unsigned int* bits = nullptr;
@@ -860,7 +924,8 @@ inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out) {
   out->inv_scale = ldexpf(1.0f, -shift);
   if (cudaMalloc(&out->hi, sizeof(__half) * cnt) != cudaSuccess) return 1;
   if (cudaMalloc(&out->lo, sizeof(__half) * cnt) != cudaSuccess) return 1;
-  tc_split_kernel<<<256, 256>>>(w_dev, out->hi, out->lo, cnt / 4, ldexpf(1.0f, shift));
+  const TcRz rz = tc_rz();
+  tc_split_weight_kernel<<<256, 256>>>(w_dev, out->hi, out->lo, n, k, ldexp(1.0, shift), rz.alpha, rz.beta, rz.beta_att, q_rows);
   if (cudaDeviceSynchronize() != cudaSuccess) return 1;
   if (tc_make_map(&out->map_hi, out->hi, n, k, out->bn)) return 2;
   if (tc_make_map(&out->map_lo, out->lo, n, k, out->bn)) return 2;
@@ -880,10 +945,15 @@ inline void tc_split(const float* src, TcPlane* dst, int rows, int cols, int mod
   tc_split_kernel<<<blocks, 256, 0, st>>>(src, dst->hi, mode == 1 /*FD_GEMM_TC_3X*/ ? dst->lo : nullptr, n4, 1.0f);
 }
 
+inline std::mutex& tc_cfg_mutex() {  // guards the per-device one-time state below (handles may live on several threads)
+  static std::mutex m;
+  return m;
+}
 inline int* tc_err_flag() {  // one flag per device (a process may own several handles on several GPUs)
   static int* flags[64] = {nullptr};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(tc_cfg_mutex());
   if (!flags[dev]) {
     if (cudaMalloc(&flags[dev], sizeof(int)) != cudaSuccess) return nullptr;
     cudaMemset(flags[dev], 0, sizeof(int));
@@ -894,6 +964,7 @@ inline int* tc_err_flag() {  // one flag per device (a process may own several h
 inline bool tc_need_configure(unsigned long long* seen_mask) {
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(tc_cfg_mutex());
   const unsigned long long bit = 1ull << (dev & 63);
   if (*seen_mask & bit) return false;
   *seen_mask |= bit;
@@ -940,11 +1011,13 @@ int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const f
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // common.cuh: PDL contract
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   __half* c_hi = c_tc ? c_tc->hi : nullptr;
   __half* c_lo = (c_tc && NPASS > 1) ? c_tc->lo : nullptr;
   const CUtensorMap& wh = CL > 1 ? w->half_hi : w->map_hi;
@@ -1019,11 +1092,13 @@ int tc_gemm_ln_launch(const TcPlane* a, const TcWeight* w, const float* bias, co
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, w->half_hi, w->half_lo, bias, resid, gamma, beta,
                                      eps, scratch, out, o_tc->hi, NPASS > 1 ? o_tc->lo : (__half*)nullptr, M, K,
                                      w->inv_scale, err);

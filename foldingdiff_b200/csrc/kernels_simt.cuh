@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace fd {
 
@@ -31,6 +32,8 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
              const float* __restrict__ temb, int temb_stride, float* __restrict__ h_out,
              __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
   constexpr int H = VPL * 32;
+  pdl_trigger();
+  pdl_wait();  // x is the previous step's output; h / planes were read by the previous step's kernels
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_rows) return;
@@ -84,6 +87,8 @@ layernorm_kernel(const float* __restrict__ in, const float* __restrict__ resid, 
                  const float* __restrict__ bta, float eps, float* __restrict__ out,
                  __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
   constexpr int H = VPL * 32;
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_rows) return;
@@ -315,6 +320,13 @@ struct StepCoef {
   float c1, beta, s, sigma;
   int add_noise;  // t > 0
 };
+// Source of the step's normals z (sampling.py:73): the caller's draws (z != nullptr: slice of the step) or, in the
+// throughput mode, element `offset + b * n_pad * F + n * F + f` of the library's Philox stream `seed` - the same
+// element fd_randn would have written there, so the two paths agree bit for bit.
+struct StepNoise {
+  const float* z;
+  unsigned long long seed, offset;
+};
 
 template <int VPL, bool SAMPLE>
 __global__ void __launch_bounds__(256)
@@ -322,12 +334,14 @@ tail_kernel(const float* __restrict__ u, const int* __restrict__ row_src, int n_
             const float* __restrict__ g, const float* __restrict__ bta, float eps_ln,
             const float* __restrict__ w2, const float* __restrict__ b2,
             float* __restrict__ eps_out,                         // MODE_EPS
-            float* __restrict__ x, const float* __restrict__ z,  // MODE_SAMPLE
+            float* __restrict__ x, StepNoise noise,              // MODE_SAMPLE
             float* __restrict__ hist, StepCoef coef, uint32_t wrap_bits) {
   constexpr int H = VPL * 32;
+  pdl_trigger();
   extern __shared__ __align__(16) float w2s[];  // [F][H]
-  for (int i = threadIdx.x; i < F * H; i += blockDim.x) w2s[i] = w2[i];
+  for (int i = threadIdx.x; i < F * H; i += blockDim.x) w2s[i] = w2[i];  // weights: no dependence on the chain
   __syncthreads();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_rows) return;
@@ -366,7 +380,10 @@ tail_kernel(const float* __restrict__ u, const int* __restrict__ row_src, int n_
     } else {
       const float xv = x[idx];
       float y = __fmul_rn(coef.c1, __fsub_rn(xv, __fdiv_rn(__fmul_rn(coef.beta, mine), coef.s)));
-      if (coef.add_noise) y = __fadd_rn(y, __fmul_rn(coef.sigma, z[idx]));
+      if (coef.add_noise) {
+        const float zv = noise.z ? noise.z[idx] : philox_normal(noise.seed, noise.offset + idx);
+        y = __fadd_rn(y, __fmul_rn(coef.sigma, zv));
+      }
       if ((wrap_bits >> lane) & 1u) y = wrap_pi(y);
       x[idx] = y;
       if (hist) hist[idx] = y;

@@ -41,7 +41,7 @@ def sharded_final_angles(run_fn: Callable[[List[int], torch.Tensor], torch.Tenso
     rank, world = _world(group)
     B = len(lengths)
     mine = shard_indices(B, rank, world)
-    local = run_fn([int(lengths[i]) for i in mine], noise[mine])
+    local = run_fn([int(lengths[i]) for i in mine], noise[mine])  # (0, N, F) when this rank has no chain
     if world == 1:
         return local.cpu()
     per_rank = (B + world - 1) // world
@@ -58,27 +58,41 @@ def sharded_final_angles(run_fn: Callable[[List[int], torch.Tensor], torch.Tenso
 
 
 def sample_final_sharded(model, lengths: Sequence[int], noise: torch.Tensor, timesteps: int,
-                         betas: torch.Tensor, is_angle, group=None) -> torch.Tensor:
-    """Multi-GPU `p_sample_loop(..., history="final")[-1]`: (B, N, F) final angles on every rank."""
+                         betas: torch.Tensor, is_angle, group=None, rng: str = "parity") -> torch.Tensor:
+    """
+    Multi-GPU `p_sample_loop(..., history="final")[-1]`: (B, N, F) final angles on every rank.
+
+    rng="parity" (SURVEY.md section 8e): every rank draws each step's normals for the WHOLE batch from its device
+    generator and keeps its own rows, so with the same device seed on every rank the result equals the single-GPU
+    `p_sample_loop` on that seed bit for bit.  rng="perf": each rank draws only its own rows (seed the ranks apart).
+    """
     from . import sampling
+
+    rank, world = _world(group)
+    shard = sampling.NoiseShard(len(lengths), shard_indices(len(lengths), rank, world)) if rng == "parity" else None
+    assert rng in ("parity", "perf"), rng
 
     def run(local_lengths, local_noise):
         dev = next(model.parameters()).device
         out = sampling.p_sample_loop(model, local_lengths, local_noise, timesteps, betas, is_angle=is_angle,
-                                     disable_pbar=True, history="final")
+                                     disable_pbar=True, history="final", noise_shard=shard)
         return out[-1].to(dev)
 
     return sharded_final_angles(run, lengths, noise, group=group)
 
 
 def sample_sharded(model, train_dset, n: int = 10, sweep_lengths=(50, 128), batch_size: int = 512,
-                   feature_key: str = "angles", seed: Optional[int] = None, group=None):
+                   feature_key: str = "angles", seed: Optional[int] = None, group=None, rng: str = "parity"):
     """
     Multi-GPU counterpart of `sampling.sample(..., history="final")`: every rank builds the same length list and
     draws the same initial noise (same CPU seed), samples its round-robin share of each batch chunk, and one
     all-gather per chunk returns the final angles in the reference's order.  Returns, on every rank, the list of
     `(length, n_features)` arrays with the training mean offset added and angular columns re-wrapped, exactly as
     `sampling.sample` post-processes them (reference sampling.py:205-222).
+
+    rng="parity" (default): `torch.manual_seed(seed)` on every rank and whole-batch step draws sliced per rank:
+    `sample_sharded(world = N, seed)` == `sampling.sample(seed, history="final")` on one GPU, bit for bit.
+    rng="perf": per-rank device streams `seed + 1000003 * rank`, each rank draws only its own rows.
     """
     import numpy as np
 
@@ -90,17 +104,17 @@ def sample_sharded(model, train_dset, n: int = 10, sweep_lengths=(50, 128), batc
     lengths = [l for l in range(lo, hi) for _ in range(n)]
     rank, _ = _world(group)
     if seed is not None:
-        torch.manual_seed(seed)  # identical initial noise on every rank (CPU generator)
-        if torch.cuda.is_available():
-            # ... but an independent stream of per-step normals per rank: with the same device seed, chain k of
-            # every rank would be driven by the same z_t sequence
+        torch.manual_seed(seed)  # identical initial noise on every rank (CPU generator); seeds the device too
+        if rng == "perf" and torch.cuda.is_available():
+            # an independent stream of per-step normals per rank: with the same device seed and per-rank draws,
+            # chain k of every rank would be driven by the same z_t sequence
             torch.cuda.manual_seed(seed + 1000003 * rank)
     out = []
     for chunk in utils.seq_to_groups(lengths, batch_size):
         noise = train_dset.sample_noise(torch.zeros((len(chunk), train_dset.pad, model.n_inputs), dtype=torch.float32))
         noise = noise[:, : max(chunk), :]
         final = sample_final_sharded(model, chunk, noise, train_dset.timesteps, train_dset.alpha_beta_terms["betas"],
-                                     train_dset.feature_is_angular[feature_key], group=group)
+                                     train_dset.feature_is_angular[feature_key], group=group, rng=rng)
         out.extend(final[i, :l].numpy() for i, l in enumerate(chunk))
     inner = getattr(train_dset, "dset", None)
     if inner is not None and hasattr(inner, "get_masked_means") and inner.get_masked_means() is not None:

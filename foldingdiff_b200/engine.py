@@ -105,6 +105,8 @@ class Engine:
         _native.check(self.lib.fd_create(C.byref(dims), arr, len(host), tt.data_ptr(), coef.data_ptr(),
                                          index, _native.GEMM_MODES[gemm], C.byref(handle)), "fd_create")
         self._h = handle
+        # the C entry points restore the caller's CUDA device themselves (include/foldingdiff_b200.h, Conventions);
+        # `with torch.cuda.device(...)` below only makes torch's current STREAM the one of the handle's device
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -133,7 +135,8 @@ class Engine:
         assert coef.shape[0] >= T, f"betas has {coef.shape[0]} entries, need {T}"
         coef = coef[:T].contiguous()
         table = self._time_rows_fn(torch.arange(T))
-        _native.check(self.lib.fd_set_schedule(self._h, T, table.data_ptr(), coef.data_ptr()), "fd_set_schedule")
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fd_set_schedule(self._h, T, table.data_ptr(), coef.data_ptr()), "fd_set_schedule")
         self._schedule_key = key
         self.timesteps = T
 
@@ -173,6 +176,23 @@ class Engine:
         with torch.cuda.device(self.device):
             _native.check(self.lib.fd_p_sample_steps(self._h, x.data_ptr(), int(t_hi), int(t_lo), _ptr(noise),
                                                      _ptr(history), wm, _stream()), "fd_p_sample_steps")
+
+    def p_sample_steps_philox(self, x: torch.Tensor, t_hi: int, t_lo: int, seed: int, offset: int,
+                              history: Optional[torch.Tensor], wrap_mask: Sequence[bool]):
+        """Throughput mode: the step kernel draws its own normals (library Philox stream `seed`, element `offset`
+        onwards) - no per-step host work, no noise tensor in HBM."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert history is None or (history.is_cuda and history.dtype == torch.float32 and history.is_contiguous())
+        wm = (C.c_uint8 * self.n_features)(*[1 if w else 0 for w in wrap_mask])
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fd_p_sample_steps_philox(self._h, x.data_ptr(), int(t_hi), int(t_lo), int(seed),
+                                                            int(offset), _ptr(history), wm, _stream()),
+                          "fd_p_sample_steps_philox")
+
+    def check_status(self):
+        """Raise NativeError if a tensor-core pipeline of an earlier asynchronous call timed out.  Call after the
+        stream has been synchronised (the loop does, wherever it hands results to the caller)."""
+        _native.check(self.lib.fd_status(self._h), "fd_status")
 
     def sample_host(self, lengths, x0: np.ndarray, t_start: int, noise: Optional[np.ndarray], seed: int,
                     wrap_mask, full_history: bool) -> np.ndarray:

@@ -35,6 +35,19 @@ from . import modelling, utils
 # reverse steps handed to the device per native call (bounds the pre-drawn noise buffer)
 STEP_WINDOW = int(os.environ.get("FOLDINGDIFF_B200_STEP_WINDOW", "50"))
 
+# Where the per-step normals come from (extension; the reference has exactly one way, torch.randn_like on the device
+# generator, sampling.py:73 - that is "torch", the default and the parity mode).  "philox": the step kernel draws them
+# from the library's counter-based stream (fd_p_sample_steps_philox) - no per-step host work and no noise tensor in
+# HBM; seeded from torch's CPU generator once per loop, so torch.manual_seed still makes runs reproducible, but the
+# values are NOT torch's.
+NOISE_SOURCE = os.environ.get("FOLDINGDIFF_B200_NOISE", "torch")
+
+
+def set_noise_source(source: str) -> None:
+    global NOISE_SOURCE
+    assert source in ("torch", "philox"), source
+    NOISE_SOURCE = source
+
 
 def _engine_for(model: nn.Module):
     if not hasattr(model, "native_engine"):
@@ -78,8 +91,34 @@ def p_sample(model: nn.Module, x: torch.Tensor, t: torch.Tensor, seq_lens: Seque
     return out
 
 
+class NoiseShard:
+    """
+    Parity-mode RNG of a chain-sharded run: this process holds rows `rows` of a global
+    batch of `global_batch` chains.  Every step it draws the FULL `(global_batch, N, F)` tensor from the device
+    generator - the very draw the single-GPU loop makes (reference sampling.py:73) - and keeps its own rows, so N
+    ranks seeded alike reproduce the 1-GPU run bit for bit.  (The draw is ~3 M normals per step at 8 x 512 chains:
+    microseconds.)
+    """
+
+    def __init__(self, global_batch: int, rows: Sequence[int]):
+        self.global_batch = int(global_batch)
+        self.rows = [int(r) for r in rows]
+        self._idx = None
+        self._full = None
+
+    def draw(self, out: torch.Tensor) -> None:
+        """Fill `out` (B_local, N, F) with this shard's rows of the next global draw."""
+        shape = (self.global_batch,) + tuple(out.shape[1:])
+        if self._full is None or self._full.shape != shape or self._full.device != out.device:
+            self._full = torch.empty(shape, device=out.device, dtype=out.dtype)
+            self._idx = torch.as_tensor(self.rows, device=out.device, dtype=torch.long)
+        _draw_normal(self._full)
+        if len(self.rows):
+            torch.index_select(self._full, 0, self._idx, out=out)
+
+
 def _run_steps(eng, x: torch.Tensor, t_start: int, wrap: Sequence[bool],
-               history: Optional[torch.Tensor]) -> None:
+               history: Optional[torch.Tensor], shard: Optional[NoiseShard] = None) -> None:
     """
     Steps t = t_start-1 .. 0 in windows of STEP_WINDOW reverse steps; draws each step's normals like
     `torch.randn_like(x)`.  `history`, if given, is a HOST tensor (t_start, B, N, F), ideally pinned: each
@@ -90,6 +129,8 @@ def _run_steps(eng, x: torch.Tensor, t_start: int, wrap: Sequence[bool],
     B, N, F = x.shape
     dev = x.device
     stage, copied, side = None, None, None
+    philox = NOISE_SOURCE == "philox" and shard is None
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if philox else 0  # one draw from torch's CPU generator
     if history is not None:
         w = min(STEP_WINDOW, t_start)
         stage = [torch.zeros((w, B, N, F), device=dev, dtype=torch.float32) for _ in range(2)]
@@ -99,17 +140,26 @@ def _run_steps(eng, x: torch.Tensor, t_start: int, wrap: Sequence[bool],
     while done < t_start:
         t_hi = t_start - done
         n = min(STEP_WINDOW, t_hi)
-        z = torch.empty((n, B, N, F), device=dev, dtype=torch.float32)
-        for k in range(n):
+        z = None if philox else torch.empty((n, B, N, F), device=dev, dtype=torch.float32)
+        for k in range(n if not philox else 0):
             if t_hi - 1 - k > 0:  # the reference draws nothing at t == 0
-                _draw_normal(z[k])
+                if shard is None:
+                    _draw_normal(z[k])
+                else:
+                    shard.draw(z[k])
+        if B == 0:  # a rank without chains in this chunk only keeps its generator in step with the others
+            done += n
+            continue
         hist_dev = None
         if history is not None:
             buf = win & 1
             if copied[buf] is not None:
                 torch.cuda.current_stream(dev).wait_event(copied[buf])  # its previous contents are on the host
             hist_dev = stage[buf][:n]
-        eng.p_sample_steps(x, t_hi, t_hi - n, z, hist_dev, wrap)
+        if philox:
+            eng.p_sample_steps_philox(x, t_hi, t_hi - n, seed, done * B * N * F, hist_dev, wrap)
+        else:
+            eng.p_sample_steps(x, t_hi, t_hi - n, z, hist_dev, wrap)
         if history is not None:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(dev))
@@ -122,16 +172,20 @@ def _run_steps(eng, x: torch.Tensor, t_start: int, wrap: Sequence[bool],
         win += 1
     if side is not None:
         side.synchronize()
+        eng.check_status()  # the history is complete on the host: a timed-out pipeline must not pass silently
 
 
 @torch.no_grad()
 def p_sample_loop(model: nn.Module, lengths: Sequence[int], noise: torch.Tensor, timesteps: int,
                   betas: torch.Tensor, is_angle: Union[bool, List[bool]] = [False, True, True, True],
-                  disable_pbar: bool = False, history: str = "full") -> torch.Tensor:
+                  disable_pbar: bool = False, history: str = "full",
+                  noise_shard: Optional[NoiseShard] = None) -> torch.Tensor:
     """
     Returns a CPU tensor of shape (timesteps, batch_size, seq_len, n_ft): entry k is the state after
     the k-th reverse step, entry -1 is x_0.  `history="final"` (extension) returns only that last
     entry, shape (1, batch, seq_len, n_ft), so `result[-1]` means the same thing either way.
+    `noise_shard` (extension, distributed.py): draw each step's normals for a global batch and keep this
+    process's rows.
     """
     device = next(model.parameters()).device
     eng = _engine_for(model)
@@ -139,17 +193,20 @@ def p_sample_loop(model: nn.Module, lengths: Sequence[int], noise: torch.Tensor,
     x = noise.detach().to(device=device, dtype=torch.float32).contiguous().clone()
     B, N, F = x.shape
     logging.info(f"Starting from noise {tuple(noise.shape)} with angularity {is_angle} using {device}")
-    eng.set_batch([int(l) for l in lengths], N)
+    if B > 0:
+        eng.set_batch([int(l) for l in lengths], N)
     wrap = _wrap_mask(is_angle, F)
     if history == "full":
         # pinned host memory (torch's caching host allocator recycles it across calls); padded rows stay 0
         hist = torch.empty((timesteps, B, N, F), dtype=torch.float32, pin_memory=True)  # every element is copied over
-        _run_steps(eng, x, timesteps, wrap, hist)
+        _run_steps(eng, x, timesteps, wrap, hist, noise_shard)
         return hist
     assert history == "final", history
-    _run_steps(eng, x, timesteps, wrap, None)
+    _run_steps(eng, x, timesteps, wrap, None, noise_shard)
     valid = torch.arange(N, device=device)[None, :] < torch.as_tensor(list(lengths), device=device)[:, None]
-    return (x * valid[..., None]).unsqueeze(0).cpu()
+    out = (x * valid[..., None]).unsqueeze(0).cpu()  # synchronises
+    eng.check_status()
+    return out
 
 
 def sample(model: nn.Module, train_dset, n: int = 10, sweep_lengths: Optional[Tuple[int, int]] = (50, 128),
@@ -180,7 +237,11 @@ def sample(model: nn.Module, train_dset, n: int = 10, sweep_lengths: Optional[Tu
                                 betas=train_dset.alpha_beta_terms["betas"],
                                 is_angle=train_dset.feature_is_angular[feature_key],
                                 disable_pbar=disable_pbar, history=history)
-        out.extend(sampled[:, i, :l, :].numpy() for i, l in enumerate(chunk))
+        # np.array(...): each chain's trimmed slice is copied into pageable memory, so the (pinned, up to ~2 GB)
+        # history block goes back to torch's host allocator after every chunk instead of staying page-locked for
+        # as long as the caller keeps the list (the reference returns views of a pageable tensor, sampling.py:201)
+        out.extend(np.array(sampled[:, i, :l, :].numpy()) for i, l in enumerate(chunk))
+        del sampled
     inner = getattr(train_dset, "dset", None)
     if inner is not None and hasattr(inner, "get_masked_means") and inner.get_masked_means() is not None:
         means = inner.get_masked_means()
@@ -221,6 +282,8 @@ def denoise_from(model: nn.Module, corrupted: torch.Tensor, lengths: Sequence[in
     x = corrupted.detach().to(device=device, dtype=torch.float32).contiguous().clone()
     eng.set_batch([int(l) for l in lengths], x.shape[1])
     _run_steps(eng, x, noise_timesteps, [True] * x.shape[-1], None)
+    torch.cuda.current_stream(device).synchronize()
+    eng.check_status()
     return x
 
 

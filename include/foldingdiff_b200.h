@@ -18,6 +18,9 @@
  *   fd_p_sample_steps    <- sampling.p_sample + the body of sampling.p_sample_loop
  *                           (foldingdiff/sampling.py:28-75, 102-131) and the inner loop of
  *                           sampling.get_reconstruction_error (:319-330)
+ *   fd_p_sample_steps_philox  same steps, normals drawn inside the step kernel from the library's
+ *                           counter-based stream (the throughput mode of SURVEY.md section 8b: no
+ *                           per-step host work at all; NOT torch's stream)
  *   fd_sample_host       <- sampling.p_sample_loop as called with host tensors
  *                           (foldingdiff/sampling.py:79-132): host in, host out
  *   fd_destroy           <- (garbage collection of the nn.Module)
@@ -32,6 +35,13 @@
  *     given CUDA stream (a cudaStream_t passed as void*; NULL = legacy default stream) and
  *     the call returns without synchronising.  fd_sample_host synchronises.
  *   - a handle is bound to one device and is not re-entrant: one in-flight call per handle.
+ *     Every entry point restores the caller's current CUDA device before it returns.
+ *   - asynchronous failures: the tensor-core pipelines never spin forever - a bounded wait that
+ *     expires (possible on a preempted / time-sliced GPU) ends the kernel and raises a
+ *     device-side flag.  fd_forward / fd_p_sample_steps* copy that flag to the host behind
+ *     their kernels; it is reported as FD_ERR_CUDA by the NEXT compute call on the handle, by
+ *     fd_sample_host before it returns, and by fd_status() - call fd_status() after
+ *     synchronising the stream and before trusting the results of an asynchronous call.
  *   - there is NO CPU fallback: every compute entry point returns FD_ERR_CUDA if no
  *     sm_100 device is usable.
  */
@@ -44,7 +54,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 enum {
   FD_OK = 0,
@@ -174,6 +184,24 @@ int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, floa
 int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
                           const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
                           void* stream);
+
+/*
+ * fd_p_sample_steps with the library as the noise source: step k (t = t_hi-1-k) adds
+ * sigma_t * z where z[b, n, f] is element  offset + k * batch * n_pad * F + (b * n_pad + n) * F + f
+ * of the Philox4x32-10 / Box-Muller stream `seed` - the element fd_randn(seed, offset) writes at
+ * that index, so pre-drawing with fd_randn and passing noise_dev gives the same bits.  A caller
+ * that splits a chain into windows passes offset = (steps already done) * batch * n_pad * F.
+ */
+int32_t fd_p_sample_steps_philox(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo, uint64_t seed,
+                                 uint64_t offset, float* history_dev, const uint8_t* wrap_mask,
+                                 void* stream);
+
+/*
+ * Asynchronous-failure check (see Conventions): FD_OK, or FD_ERR_CUDA if a tensor-core pipeline
+ * of a previous call on this handle timed out (its results are invalid).  Does not synchronise:
+ * call it after synchronising the stream the work was enqueued on.  Reading clears the condition.
+ */
+int32_t fd_status(fd_handle* h);
 
 /*
  * Host-buffer convenience for non-Python callers: the whole p_sample_loop.

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol():
 
 def test_version_and_counts():
     lib = _native.lib()
-    assert lib.fd_abi_version() == 1
+    assert lib.fd_abi_version() == 2
     assert lib.fd_num_weights(12) == 4 + 17 * 12 + 6
     assert b"sm_100a" in lib.fd_build_info()
     assert lib.fd_last_error() is not None

@@ -25,6 +25,27 @@ def test_single_process_passthrough():
     assert torch.equal(out, noise * 2)
 
 
+def test_noise_shard_rows_of_the_global_draw():
+    """Parity-mode RNG: each rank draws the whole batch's normals and keeps its rows; the ranks' rows
+    stitched together are the single-process draws, step after step, and an empty shard still advances the stream."""
+    from foldingdiff_b200 import sampling
+    B, N, F, steps = 5, 7, 6, 3
+    torch.manual_seed(3)
+    ref = [torch.randn(B, N, F) for _ in range(steps)]
+    for world in (2, 8):  # 8 > B: ranks 5..7 hold no chain
+        got = [torch.zeros(B, N, F) for _ in range(steps)]
+        for rank in range(world):
+            rows = fdist.shard_indices(B, rank, world)
+            shard = sampling.NoiseShard(B, rows)
+            torch.manual_seed(3)
+            for k in range(steps):
+                z = torch.empty(len(rows), N, F)
+                shard.draw(z)
+                got[k][rows] = z
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)
+
+
 WORKER = textwrap.dedent("""
     import os, sys, torch
     import torch.distributed as dist

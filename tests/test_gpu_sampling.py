@@ -248,3 +248,61 @@ def test_sample_sharded_single_rank_equals_sample(mini_dir):
     assert len(ref) == len(got) == 12
     for r, g in zip(ref, got):
         np.testing.assert_array_equal(r[-1], g)
+
+
+def test_philox_steps_equal_predrawn_library_noise(mini_dir):
+    """fd_p_sample_steps_philox (normals drawn inside the step kernel) == fd_p_sample_steps fed with fd_randn's draws of
+    the same (seed, offset): one stream, two ways to consume it - also across a window split."""
+    from foldingdiff_b200 import _native
+    model = mini_model(mini_dir, "tc3x")
+    eng = model.native_engine()
+    T, lengths, N = 9, [33, 40, 17], 40
+    eng.set_schedule(beta_schedules.get_variance_schedule("linear", T), T)
+    eng.set_batch(lengths, N)
+    x0 = oloop.wrap(torch.randn(3, N, 6, generator=torch.Generator().manual_seed(4))).cuda()
+    seed, slice_ = 987654321, 3 * N * 6
+    z = torch.empty(T, 3, N, 6, device="cuda")
+    _native.check(_native.lib().fd_randn(z.data_ptr(), z.numel(), seed, 0, None), "fd_randn")
+    torch.cuda.synchronize()
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05
+    a, b, c = x0.clone(), x0.clone(), x0.clone()
+    ha, hb = torch.zeros(T, 3, N, 6, device="cuda"), torch.zeros(T, 3, N, 6, device="cuda")
+    eng.p_sample_steps(a, T, 0, z, ha, ANG)
+    eng.p_sample_steps_philox(b, T, 0, seed, 0, hb, ANG)
+    eng.p_sample_steps_philox(c, T, T - 4, seed, 0, None, ANG)            # window 1: steps 0..3
+    eng.p_sample_steps_philox(c, T - 4, 0, seed, 4 * slice_, None, ANG)   # window 2 continues the stream
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert torch.equal(a, b) and torch.equal(ha, hb) and torch.equal(a, c)
+    # the Python loop in throughput mode: reproducible under torch.manual_seed, different from the torch stream
+    try:
+        sampling.set_noise_source("philox")
+        torch.manual_seed(3)
+        p1 = sampling.p_sample_loop(model, lengths, x0.cpu(), T, beta_schedules.get_variance_schedule("linear", T), is_angle=ANG)
+        torch.manual_seed(3)
+        p2 = sampling.p_sample_loop(model, lengths, x0.cpu(), T, beta_schedules.get_variance_schedule("linear", T), is_angle=ANG)
+    finally:
+        sampling.set_noise_source("torch")
+    assert torch.equal(p1, p2) and float(p1.abs().max()) <= np.pi and p1.shape == (T, 3, N, 6)
+
+
+def test_parity_rng_sharded_ranks_reproduce_the_single_gpu_run(mini_dir):
+    """SURVEY 8e parity mode: every rank draws the whole batch's step normals and keeps its rows.  Two (and five: more
+    ranks than some shards have chains) ranks simulated one after the other on this GPU, seeded alike, stitch together
+    to the single-GPU sample bit for bit."""
+    from foldingdiff_b200 import distributed as fdist
+    model = mini_model(mini_dir, "tc3x")
+    T, lengths = 12, [20, 22, 24, 26, 28]
+    betas = beta_schedules.get_variance_schedule("cosine", T)
+    noise = oloop.wrap(torch.randn(5, 28, 6, generator=torch.Generator().manual_seed(8)))
+    torch.manual_seed(21)
+    ref = sampling.p_sample_loop(model, lengths, noise, T, betas, is_angle=ANG, history="final")[-1]
+    for world in (2, 7):
+        got = torch.zeros_like(ref)
+        for rank in range(world):
+            rows = fdist.shard_indices(5, rank, world)
+            torch.manual_seed(21)
+            loc = sampling.p_sample_loop(model, [lengths[i] for i in rows], noise[rows], T, betas, is_angle=ANG,
+                                         history="final", noise_shard=sampling.NoiseShard(5, rows))[-1]
+            got[rows] = loc
+        assert torch.equal(got, ref), f"world={world}: max diff {float((got - ref).abs().max()):.3e}"
