@@ -40,16 +40,38 @@ from foldingdiff_b200 import beta_schedules, datasets, synthetic  # noqa: E402
 
 SEED = 7344
 PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
-# From the committed `ncu --set full` capture of this configuration (profiles/r01_gemm_ncu.md, config 2,
-# FD_GEMM_TC_3X, CTA-pair mode): dram__bytes_read.sum + dram__bytes_write.sum per launch, and
-# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active.  Static annotations, not re-measured here.
-NCU_GEMM = {
-    "dram_bytes_per_launch": {"gemm_qkv": 226.2e6, "gemm_attn_out": 82.4e6, "gemm_ffn1": 155.6e6, "gemm_ffn2": 153.1e6},
-    "tensor_pipe_active_pct": {"gemm_qkv": 75.8, "gemm_attn_out": 66.2, "gemm_ffn1": 62.1, "gemm_ffn2": 79.5,
-                               "attention_tc": 18.6},
-    "source": "profiles/r01_gemm_ncu.md, profiles/r01_attention_tc_ncu.md",
-}
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 FALLBACK_PEAK_TFLOPS = 1590.0  # /opt/skills/guides/B200_PROFILING.md fallback (burst)
+
+
+def source_sha():
+    """Hash of the CUDA sources (tools/summarize_ncu.py computes the same one when it summarises an ncu capture)."""
+    import hashlib
+    csrc = os.path.join(ROOT, "foldingdiff_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".hpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(csrc, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_ncu_profile():
+    """
+    The newest committed per-step ncu summary (profiles/rNN_step_ncu.json, written by tools/summarize_ncu.py step from a
+    capture of tools/gpu_ncu_step.sh): DRAM bytes and tensor-pipe activity per kernel category.  ncu figures cannot be
+    taken inside a timed run, so they are annotations - but self-describing ones: the file names the source hash it was
+    captured from, and a mismatch with the sources of THIS run is reported as `stale` instead of passing silently.
+    """
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_ncu.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        prof = json.load(f)
+    prof["file"] = os.path.relpath(files[-1], ROOT)
+    prof["stale"] = prof.get("source_sha") != source_sha()
+    return prof
 
 
 def parse_args():
@@ -68,6 +90,8 @@ def parse_args():
     p.add_argument("--cpu-chains", type=int, default=64)
     p.add_argument("--cpu-steps", type=int, default=3)
     p.add_argument("--profile-steps", type=int, default=20, help="reverse steps of the CUDA-event kernel profile")
+    p.add_argument("--no-extra-workloads", action="store_true", help="skip the short config 3 / config 5 sub-lines")
+    p.add_argument("--no-parity", action="store_true", help="skip the parity block")
     return p.parse_args()
 
 
@@ -181,7 +205,10 @@ def _cpu_model():
     return _CPU_MODEL
 
 
-def _cpu_steps(sub, n_pad, T, start_t, steps, threads):
+_CPU_TRACE = None  # states of the last reference-arm run: {"x": [x_init, x_1, ...], "t": [...], "seed": int, "sub": lengths}
+
+
+def _cpu_steps(sub, n_pad, T, start_t, steps, threads, trace=False):
     """
     seconds per reverse step of the reference's CPU path on `threads` host threads (1 untimed warm-up step).
     With baseline/_ref: the stock `sampling.p_sample` + per-column `utils.modulo_with_wrapped_range` + `.cpu()` of the
@@ -191,10 +218,14 @@ def _cpu_steps(sub, n_pad, T, start_t, steps, threads):
     model = _cpu_model()
     ref = _reference()
     g = torch.Generator().manual_seed(SEED)
+    global _CPU_TRACE
     if ref:
         sampling, beta_schedules, utils = ref[:3]
         betas = beta_schedules.get_variance_schedule("cosine", T)
         x = torch.randn(len(sub), n_pad, 6, generator=g)
+        if trace:  # the reference draws its step normals from the global CPU generator: seed it so the GPU can replay them
+            torch.manual_seed(SEED + 1)
+            _CPU_TRACE = {"x": [x.clone()], "t": [], "seed": SEED + 1, "sub": list(sub), "n_pad": n_pad}
 
         def step(img, i):
             with torch.no_grad():
@@ -205,19 +236,34 @@ def _cpu_steps(sub, n_pad, T, start_t, steps, threads):
             img.cpu()
             return img
         x = step(x, start_t - 1)
-        t0 = time.perf_counter()
+        if trace:
+            _CPU_TRACE["x"].append(x.clone()); _CPU_TRACE["t"].append(start_t - 1)
+        dt = 0.0
         for k in range(steps):  # per-step cost does not depend on t
+            t0 = time.perf_counter()
             x = step(x, start_t - 2 - k)
-        return (time.perf_counter() - t0) / steps
+            dt += time.perf_counter() - t0
+            if trace:
+                _CPU_TRACE["x"].append(x.clone()); _CPU_TRACE["t"].append(start_t - 2 - k)
+        return dt / steps
     from oracle import loop as oloop
     from oracle import schedules as osched
     betas = osched.betas_for("cosine", T)
     x = oloop.wrap(torch.randn(len(sub), n_pad, 6, generator=g))
+    if trace:
+        torch.manual_seed(SEED + 1)
+        _CPU_TRACE = {"x": [x.clone()], "t": [], "seed": SEED + 1, "sub": list(sub), "n_pad": n_pad}
     x = oloop.wrap(oloop.p_sample(model, x, torch.full((len(sub),), start_t - 1, dtype=torch.long), sub, betas))
-    t0 = time.perf_counter()
+    if trace:
+        _CPU_TRACE["x"].append(x.clone()); _CPU_TRACE["t"].append(start_t - 1)
+    dt = 0.0
     for k in range(steps):  # per-step cost does not depend on t
+        t0 = time.perf_counter()
         x = oloop.wrap(oloop.p_sample(model, x, torch.full((len(sub),), start_t - 2 - k, dtype=torch.long), sub, betas))
-    return (time.perf_counter() - t0) / steps
+        dt += time.perf_counter() - t0
+        if trace:
+            _CPU_TRACE["x"].append(x.clone()); _CPU_TRACE["t"].append(start_t - 2 - k)
+    return dt / steps
 
 
 _BEST_THREADS = None
@@ -244,7 +290,7 @@ def cpu_reference_rate(lengths, n_pad, T, chains, steps, start_t, wrap_all):
         cands = sorted({c for c in (cores, 64, 32, 16) if c <= cores}, reverse=True)
         probe = {c: _cpu_steps(sub, n_pad, T, start_t, 1, c) for c in cands}
         _BEST_THREADS = min(probe, key=probe.get)
-    dt = _cpu_steps(sub, n_pad, T, start_t, steps, _BEST_THREADS)
+    dt = _cpu_steps(sub, n_pad, T, start_t, steps, _BEST_THREADS, trace=True)
     rate = len(sub) / (dt * start_t)
     what = ("stock sampling.p_sample + wrap of the reference installed in baseline/_ref around its own GaussianFourierProjection / "
             "BertEmbeddings / AnglesPredictor and the installed transformers' relative_key attention + BERT blocks (4.11.3 is "
@@ -411,16 +457,50 @@ def main():
         att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
         dominant = "projection GEMMs (tc_gemm_kernel / sgemm_tn_kernel)" if gemm_ms >= att_ms else "relative-key attention (attention_tc_kernel / attention_simt_kernel)"
         dom_tf = gemm_tf if gemm_ms >= att_ms else att_tf
+        hbm_gbs, hbm_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        if os.path.isfile(PEAKS_FILE):
+            hbm_gbs, hbm_src = float(pk.get("hbm_gbs", FALLBACK_HBM_GBS)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        ncu = load_ncu_profile() if (args.workload == "config2" and args.gemm == "tc3x") else None
+        ncu_k = (ncu or {}).get("kernels", {})
+        gemm_cats = [k for k in ("gemm_qkv", "gemm_attn_out", "gemm_ffn1", "gemm_ffn2") if k in ncu_k]
+        traffic = None
+        if ncu and gemm_cats and gemm_ms >= att_ms:
+            traffic = float(np.mean([ncu_k[k]["dram_bytes_per_launch"] for k in gemm_cats]))
+        # per-kernel entries: the tensor-bound kernels against the tensor peak, the streaming kernels against HBM
+        per_kernel = {}
+        for k, fl in gemm_flops.items():
+            if prof[k][1]:
+                tf = fl / (prof[k][0] / nprof * 1e-3) / 1e12
+                per_kernel[k] = {"bound": "tensor", "achieved_tflops": tf, "frac": tf / peak_tf,
+                                 "tensor_pipe_active_pct_ncu": ncu_k.get(k, {}).get("tensor_pipe_active_pct"),
+                                 "dram_bytes_per_launch_ncu": ncu_k.get(k, {}).get("dram_bytes_per_launch")}
+        per_kernel["attention"] = {"bound": "tensor", "achieved_tflops": att_tf, "frac": att_tf / peak_tf,
+                                   "tensor_pipe_active_pct_ncu": ncu_k.get("attention", {}).get("tensor_pipe_active_pct"),
+                                   "dram_bytes_per_launch_ncu": ncu_k.get("attention", {}).get("dram_bytes_per_launch")}
+        rows_total = float(n.sum())
+        stream_bytes = {  # algorithmic bytes per launch of the HBM-bound kernels (packed rows x hidden)
+            "embed": rows_total * (6 * 4 + H * (4 + 4)),                 # x in; h fp32 + hi/lo planes out
+            "tail_posterior": rows_total * (H * 4 + 6 * 4 * 3),          # u in; x in/out, z in
+            "layernorm": rows_total * H * (4 + 4 + 4 + 4),               # fp32 mode only: in + resid, out + planes
+        }
+        for k, by in stream_bytes.items():
+            if k in prof and prof[k][1]:
+                gbs = by / (prof[k][0] / prof[k][1] * 1e-3) / 1e9
+                per_kernel[k] = {"bound": "hbm", "achieved_gbs": gbs, "frac": gbs / hbm_gbs, "algorithmic_bytes_per_launch": by}
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": dom_tf / peak_tf, "peak_source": peak_src,
-                    "traffic": (float(np.mean(list(NCU_GEMM["dram_bytes_per_launch"].values())))
-                                if (args.workload == "config2" and args.gemm == "tc3x" and gemm_ms >= att_ms) else None),
-                    "traffic_note": "ncu DRAM bytes per GEMM launch, mean over the four projections; " + NCU_GEMM["source"],
-                    "tensor_pipe_active_pct_ncu": NCU_GEMM["tensor_pipe_active_pct"],
+                    "frac": dom_tf / peak_tf, "peak_source": peak_src, "hbm_peak_gbs": hbm_gbs, "hbm_peak_source": hbm_src,
+                    "traffic": traffic,
+                    "traffic_note": "ncu dram__bytes_read + dram__bytes_write per GEMM launch, mean over the four projections of a layer",
+                    "ncu_profile": None if not ncu else {"file": ncu["file"], "source_sha": ncu.get("source_sha"), "stale": ncu["stale"],
+                                                          "head": ncu.get("head"),
+                                                          "dram_bytes_per_reverse_step": ncu.get("dram_bytes_per_reverse_step"),
+                                                          "tensor_pipe_active_pct_time_weighted": ncu.get("tensor_pipe_active_pct_time_weighted")},
+                    "per_kernel": per_kernel,
                     "gemm_tflops_algorithmic": gemm_tf, "attention_tflops_algorithmic": att_tf,
                     "whole_step_tflops_algorithmic": flops_step * start_t / (ms_per_step * 1e-3) / 1e12,
                     "note": "algorithmic FLOPs (valid tokens, 2 flop/MAC, SURVEY 8d) / CUDA-event kernel time; "
-                            "the 3-pass split issues 3x these MMAs"}
+                            "the 3-pass split issues 3x these MMAs; ncu figures come from the committed capture named in "
+                            "ncu_profile (stale = the CUDA sources have changed since it was taken)"}
 
     # ---- section 8f rank-1 row: batched NeRF (angles -> backbone coordinates), reported beside the headline ----
     nerf_line = None
@@ -484,6 +564,109 @@ def main():
         rate, cores, sample, _ = cpu_reference_rate(lengths, n_pad, T, args.cpu_chains, args.cpu_steps, start_t, wrap_all)
         cpu_baseline = {"value": rate, "unit": "backbones/s", "cores": cores, "kind": cpu_kind(), "sample": sample}
 
+    # ---- parity block: what the number above was computed WITH, checked in the same run --------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = {"tolerance_max_abs": 1e-4, "metric": "circular max-abs over valid residues, fp32 angles"}
+        # (1) the benchmarked arithmetic against the library's fp32 CUDA-core arithmetic: whole batch, 8 reverse steps
+        #     from the middle of the schedule (the first step of a cosine chain has a x100 gain: reported separately)
+        if args.gemm != "fp32":
+            def short_chain(gemm, t_hi, nst, zz):
+                model.set_gemm(gemm)
+                xx = noise_dev.clone()
+                eng.p_sample_steps(xx, t_hi, t_hi - nst, zz, None, wrap)
+                torch.cuda.synchronize()
+                return xx
+            gz = torch.Generator(device=dev).manual_seed(5)
+            zz = torch.randn((8, B, n_pad, 6), device=dev, generator=gz)
+            valid = (torch.arange(n_pad, device=dev)[None, :] < torch.as_tensor(lengths, device=dev)[:, None])[..., None]
+            def cdiff(a, b):
+                d = (a - b).abs()
+                return float((torch.minimum(d, 2 * np.pi - d) * valid).max())
+            t_mid = max(8, min(start_t, T // 2))
+            mid = cdiff(short_chain(args.gemm, t_mid, 8, zz), short_chain("fp32", t_mid, 8, zz))
+            first = cdiff(short_chain(args.gemm, start_t, 1, zz), short_chain("fp32", start_t, 1, zz))
+            model.set_gemm(args.gemm)
+            parity["vs_fp32_cuda_cores"] = {"chains": B, "steps": 8, "from_t": t_mid, "max_abs": mid,
+                                            "first_step_from_t_start_max_abs": first, "ok": bool(mid < 1e-4)}
+        # (2) against the reference arm's own states (cpu_baseline leg: the stock loop on the host): every CPU step is
+        #     replayed on the GPU from the CPU's x_t with the CPU's normals (teacher-forced, SURVEY 8c protocol (2))
+        if cpu_baseline is not None and _CPU_TRACE is not None and len(_CPU_TRACE["t"]) >= 1:
+            tr = _CPU_TRACE
+            torch.manual_seed(tr["seed"])
+            eng.set_batch(tr["sub"], tr["n_pad"])
+            errs = []
+            for k, t in enumerate(tr["t"]):
+                zc = torch.randn_like(tr["x"][k]) if t > 0 else torch.zeros_like(tr["x"][k])  # the reference's own draw order
+                xg = tr["x"][k].to(dev).contiguous().clone()
+                eng.p_sample_steps(xg, t + 1, t, zc.to(dev)[None].contiguous(), None, wrap)
+                d = (xg.cpu() - tr["x"][k + 1]).abs()
+                d = torch.minimum(d, 2 * np.pi - d)
+                errs.append(max(float(d[i, :l].max()) for i, l in enumerate(tr["sub"])))
+            eng.set_batch(lengths, n_pad)
+            later = errs[1:] if tr["t"][0] == T - 1 and len(errs) > 1 else errs
+            parity["vs_reference_arm"] = {"kind": cpu_kind(), "chains": len(tr["sub"]), "steps": len(errs), "t": tr["t"],
+                                          "max_abs_per_step": errs, "max_abs_excluding_first_cosine_step": max(later),
+                                          "ok": bool(max(later) < 1e-4),
+                                          "note": "step k starts from the CPU arm's x_t and uses its normals; t = T-1 of the cosine "
+                                                  "schedule multiplies any forward difference by 1/sqrt(alpha_T) = 100"}
+        eng.check_status()
+
+    # ---- BASELINE configs 5 and 3 as short driver-visible sub-lines (single GPU, after everything above) ---------
+    extra = None
+    if rank == 0 and world == 1 and args.workload == "config2" and not args.no_extra_workloads:
+        extra = {}
+        def short_pass(name, lens, npad, t_from, nsteps, reps):
+            eng.set_batch(lens, npad)
+            nb = len(lens)
+            x0 = torch.randn(nb, npad, 6, device=dev).remainder(2 * np.pi) - np.pi
+            zz = torch.randn((min(nsteps, 50), nb, npad, 6), device=dev)
+            def run():
+                xx = x0.clone()
+                done = 0
+                while done < nsteps:
+                    m_ = min(50, nsteps - done)
+                    eng.p_sample_steps(xx, t_from - done, t_from - done - m_, zz[:m_], None, wrap)
+                    done += m_
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms5 = short_pass("config5", [128] * 512, 128, min(250, T), min(250, T), 2)
+        extra["config5"] = {"workload": "partial_noise_reconstruct: 512 chains x 128, denoise from t=250 (250 reverse steps, complete pass)",
+                            "ms_per_pass": ms5, "value": 512 / (ms5 / 1000.0), "unit": "backbones/s", "extrapolated": False}
+        ms3 = short_pass("config3", [128] * 4096, 128, T, 20, 1)
+        extra["config3"] = {"workload": "4096 chains x 128, T=1000: 20 reverse steps timed (per-step cost does not depend on t), x50",
+                            "ms_per_reverse_step": ms3 / 20, "value": 4096 / (ms3 / 20 * T / 1000.0), "unit": "backbones/s",
+                            "extrapolated": True,
+                            "tflops_algorithmic": synthetic.algorithmic_flops(synthetic.PRODUCTION, [128] * 4096) / (ms3 / 20 * 1e-3) / 1e12}
+        eng.set_batch(lengths, n_pad)
+        eng.check_status()
+
+    # ---- multi-GPU self-check: the sharded public path against a single-rank rerun, bit for bit -------------------
+    selfcheck = None
+    if world > 1:
+        Ts, per = 8, 32
+        lens_g = synthetic.sweep_lengths(per * world)
+        dsm = datasets.NoisedAnglesDataset(datasets.AnglesEmptyDataset("canonical-full-angles", pad=128), timesteps=Ts, beta_schedule="cosine")
+        torch.manual_seed(SEED + 2)
+        ng = dsm.sample_noise(torch.zeros(len(lens_g), 128, 6))[:, : max(lens_g)].contiguous()
+        torch.manual_seed(SEED + 3)  # same device seed on every rank: parity-mode RNG (distributed.py)
+        got = fdist.sample_final_sharded(model, lens_g, ng, Ts, dsm.alpha_beta_terms["betas"], wrap)
+        if rank == 0:
+            torch.manual_seed(SEED + 3)
+            ref1 = sampling.p_sample_loop(model, lens_g, ng, Ts, dsm.alpha_beta_terms["betas"], is_angle=wrap, history="final")[-1]
+            selfcheck = {"what": "distributed.sample_final_sharded (NCCL all-gather, parity-mode RNG) == single-rank sampling.p_sample_loop on the same seed",
+                         "chains": len(lens_g), "timesteps": Ts, "bit_identical": bool(torch.equal(got, ref1)),
+                         "max_abs_diff": float((got - ref1).abs().max())}
+        eng.set_schedule(betas, T)
+        eng.set_batch(lengths, n_pad)
+
     if rank == 0:
         line = {
             "metric": "backbones/sec", "value": value, "unit": "backbones/s", "n_gpus": world,
@@ -496,7 +679,8 @@ def main():
                        "l2": "inputs larger than L2: ~1 GB of activations per reverse step, 1000 steps per pass",
                        "algorithmic_tflop_per_pass": flops_step * start_t / 1e12},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu_baseline, "next_rows": {"nerf": nerf_line, "writers": wline},
+            "cpu_baseline": cpu_baseline, "parity": parity, "workloads": extra, "multi_gpu_selfcheck": selfcheck,
+            "next_rows": {"nerf": nerf_line, "writers": wline},
         }
         print(json.dumps(line))
     if world > 1:

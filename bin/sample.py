@@ -4,10 +4,10 @@ Sample protein backbones with the B200-native sampler.
 
 Same command line and output tree as the reference's bin/sample.py (/root/reference/bin/sample.py:237-287,
 README.md:90-96): `-m/--model -o/--outdir -n/--num -l/--lengths -b/--batchsize --fullhistory
---testcomparison --nopsea --seed --device`.  What this script does natively is the hot path
-(load -> sampling.sample -> angle CSVs); PDB writing / plots / PSEA are the reference's unchanged
-post-processing (foldingdiff.angles_and_coords, needs biotite + matplotlib) and are run only when that
-package is importable.
+--testcomparison --nopsea --seed --device`.  Native here: the hot path (load -> sampling.sample), the batched GPU
+NeRF (angles -> N / CA / C coordinates) and the output writers (sampled_angles/*.csv.gz, sampled_pdb/*.pdb,
+sampled_coords.npz), SURVEY.md section 8f rows 1-2.  Plots and the PSEA / test-set comparison of the reference need
+biotite + matplotlib + its CATH pipeline and are out of scope.
 """
 import argparse
 import json
@@ -58,25 +58,29 @@ def build_parser() -> argparse.ArgumentParser:
 def main() -> None:
     args = build_parser().parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = 0
+    rank = int(os.environ.get("RANK", "0"))
+    outdir = Path(args.outdir)
+    # every argument / output-directory check runs BEFORE the process group exists, so a bad invocation ends the job at
+    # once instead of leaving ranks blocked in a collective until the NCCL timeout
+    if not os.path.isdir(args.model):
+        raise SystemExit(f"{args.model} is not a directory; hub ids need network access, which this build does not assume")
+    if args.testcomparison:
+        raise SystemExit("--testcomparison needs the reference's CATH dataset pipeline (out of scope here)")
+    if world > 1 and args.fullhistory:
+        raise SystemExit("--fullhistory is single-GPU only")
+    if rank == 0 and os.path.isdir(outdir) and os.listdir(outdir):  # (torchrun tears the other ranks down when rank 0 exits)
+        raise SystemExit(f"Expected {outdir} to be empty!")  # the reference asserts the same (bin/sample.py:300)
     if world > 1:
         # launched with torchrun: one process per GPU, chains sharded round-robin over the ranks, one all-gather
         # of the finished angles per batch, rank 0 writes the outputs (foldingdiff_b200/distributed.py)
         import torch.distributed as dist
-        assert not args.fullhistory, "--fullhistory is single-GPU only"
         local = int(os.environ.get("LOCAL_RANK", "0"))
         args.device = f"cuda:{local}"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(args.device))
         rank = dist.get_rank()
-    outdir = Path(args.outdir)
-    if not os.path.isdir(args.model):
-        raise SystemExit(f"{args.model} is not a directory; hub ids need network access, which this build does not assume")
-    if args.testcomparison:
-        raise SystemExit("--testcomparison needs the reference's CATH dataset pipeline (out of scope here)")
     if rank == 0:
         os.makedirs(outdir, exist_ok=True)
-        assert not os.listdir(outdir), f"Expected {outdir} to be empty!"
         os.makedirs(outdir / "plots", exist_ok=True)
     train_dset = build_datasets(Path(args.model))
     model = modelling.BertForDiffusionBase.from_dir(
@@ -97,7 +101,7 @@ def main() -> None:
         torch.manual_seed(args.seed)
         sampled = sampling.sample(model, train_dset, n=args.num, sweep_lengths=(lo, hi), batch_size=args.batchsize,
                                   history="full" if args.fullhistory else "final")
-    cols = list(train_dset.feature_names["angles"])
+    cols = list(train_dset.feature_names[train_dset.dset_key])
     from foldingdiff_b200 import nerf as fnerf
     from foldingdiff_b200 import writers
     # outputs (reference tree, README.md:90-96): sampled_angles/generated_{i}.csv.gz (what DataFrame.to_csv writes),
@@ -112,12 +116,18 @@ def main() -> None:
     angles_dir, pdb_dir = outdir / "sampled_angles", outdir / "sampled_pdb"
     os.makedirs(angles_dir, exist_ok=True)
     os.makedirs(pdb_dir, exist_ok=True)
-    # backbone coordinates on the GPU (fd_nerf_build): (3 * length, 3) N/CA/C per chain
-    xyz = fnerf.build_backbone(torch.from_numpy(packed).to(args.device), lens, cols, center=True).cpu().numpy()
-    writers.write_batch(lens, angles=packed, feature_names=cols,
-                        csv_paths=[str(angles_dir / f"generated_{i}.csv.gz") for i in range(len(lens))],
-                        coords=xyz, pdb_paths=[str(pdb_dir / f"generated_{i}.pdb") for i in range(len(lens))])
-    np.savez_compressed(outdir / "sampled_coords.npz", **{f"generated_{i}": xyz[i, : 3 * lens[i]] for i in range(len(lens))})
+    csv_paths = [str(angles_dir / f"generated_{i}.csv.gz") for i in range(len(lens))]
+    writers.write_batch(lens, angles=packed, feature_names=cols, csv_paths=csv_paths)
+    if train_dset.dset_key == "angles":
+        # backbone coordinates on the GPU (fd_nerf_build): (3 * length, 3) N/CA/C per chain.  Like the reference's
+        # create_new_chain_nerf (angles_and_coords.py:112-184) a chain whose coordinates are not finite gets no PDB file.
+        xyz = fnerf.build_backbone(torch.from_numpy(packed).to(args.device), lens, cols, center=True).cpu().numpy()
+        ok = [i for i in range(len(lens)) if np.isfinite(xyz[i, : 3 * lens[i]]).all()]
+        if len(ok) < len(lens):
+            logging.warning(f"{len(lens) - len(ok)} chains have non-finite coordinates: no PDB written for them")
+        writers.write_batch([lens[i] for i in ok], coords=np.ascontiguousarray(xyz[ok]),
+                            pdb_paths=[str(pdb_dir / f"generated_{i}.pdb") for i in ok])
+        np.savez_compressed(outdir / "sampled_coords.npz", **{f"generated_{i}": xyz[i, : 3 * lens[i]] for i in ok})
     if args.fullhistory:
         hist_dir = angles_dir / "sample_history"
         for i, series in enumerate(sampled):

@@ -52,7 +52,10 @@ struct DevGuard {
 };
 
 struct LayerW {
-  float *w_qkv, *b_qkv, *b_qkv_tc = nullptr, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
+  // tensor-core path, LayerNorm folded into the projections (gemm_tc.cuh: TcLn): epilogue vectors c[n] / d[n] of the
+  // QKV projection (input LN = the previous layer's output LN; layer 0: c = 0, d = bias) and of the FFN-in projection
+  float *c_qkv = nullptr, *d_qkv = nullptr, *c_i = nullptr, *d_i = nullptr;
+  float *w_qkv, *b_qkv, *dist, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
   fd::TcWeight tq, to, ti, to2;  // tensor-core operand planes (hi / lo) of the four projections
   __half *e_hi = nullptr, *e_lo = nullptr;  // distance embedding as fp16 hi / lo, padded to 256 rows
 };
@@ -70,6 +73,9 @@ struct fd_handle {
   float *w_d1 = nullptr, *b_d1 = nullptr, *hln_g = nullptr, *hln_b = nullptr, *w_d2 = nullptr,
         *b_d2 = nullptr;
   fd::TcWeight td1;
+  float *c_d1 = nullptr, *d_d1 = nullptr;  // fold vectors of the decoder's dense1 (input LN = the last layer's output LN)
+  float2 *stats1 = nullptr, *stats2 = nullptr;  // per-row partial (sum, sum of squares) of the two LayerNorm sites
+  int stat_parts = 0;
   float* time_table = nullptr;  // (T, H) device
   std::vector<float> coef;      // (T, 4) host
 
@@ -135,7 +141,8 @@ void free_batch(fd_handle* h) {
   cudaFree(h->row_src); cudaFree(h->row_start); cudaFree(h->n_rows); cudaFree(h->n_keys);
   cudaFree(h->key_bias);
   cudaFree(h->h); cudaFree(h->qkv); cudaFree(h->ctx); cudaFree(h->tmp); cudaFree(h->a);
-  cudaFree(h->inter);
+  cudaFree(h->inter); cudaFree(h->stats1); cudaFree(h->stats2);
+  h->stats1 = h->stats2 = nullptr;
   fd::tc_free_acts(&h->tc);
   h->row_src = h->row_start = h->n_rows = h->n_keys = nullptr;
   h->key_bias = nullptr;
@@ -234,71 +241,90 @@ void launch_tail(fd_handle* H, float* eps_out, float* x, fd::StepNoise noise, fl
 // `a_tc` / `c_tc` are the tensor-core operand planes that shadow A / C (nullptr where unused).
 int project(fd_handle* H, int cat, int epi, const float* A, const float* W, const fd::TcWeight* tw,
             const float* bias, const float* resid, float* C, int N, int K, const fd::TcPlane* a_tc,
-            fd::TcPlane* c_tc, cudaStream_t st) {
+            fd::TcPlane* c_tc, cudaStream_t st, const fd::TcLn& ln = fd::TcLn()) {
   ProfScope ps(H, cat, st);
   if (H->gemm_mode == FD_GEMM_FP32_SIMT) {
     launch_sgemm(H, epi, A, W, bias, resid, C, H->rows_pad, N, K, st);
     return FD_OK;
   }
   int rc = fd::tc_gemm(H->gemm_mode, epi, a_tc, tw, bias, resid, C, c_tc, H->rows_pad, N, K,
-                       H->sm_count, st);
+                       H->sm_count, st, ln);
   if (rc != 0) return fail(FD_ERR_CUDA, "tensor-core GEMM launch failed (%d)", rc);
   H->launches++;
   return FD_OK;
 }
 
-// Fused projection + residual + LayerNorm on the tensor-core path (gemm_tc.cuh: tc_gemm_ln_kernel).
-int project_ln(fd_handle* H, int cat, const fd::TcPlane* a_tc, const fd::TcWeight* tw, const float* bias,
-               const float* resid, const float* g, const float* b, float* out, fd::TcPlane* o_tc, int K, cudaStream_t st) {
-  ProfScope ps(H, cat, st);
-  int rc = fd::tc_gemm_ln(H->gemm_mode, a_tc, tw, bias, resid, g, b, H->d.ln_eps, H->tmp, out, o_tc, H->rows_pad, K,
-                          H->sm_count, st);
-  if (rc != 0) return fail(FD_ERR_CUDA, "fused GEMM+LayerNorm launch failed (%d)", rc);
-  H->launches++;
-  return FD_OK;
-}
-
 // The noise-predictor forward on the current batch: leaves gelu(dense1(h_L)) in H->tmp.
-// fp32 mode: every tensor fp32, CUDA-core kernels.  tc modes: the residual stream (h, a, tmp) stays
-// fp32; GEMM operands travel as fp16 hi / lo planes written by the producing kernel's epilogue
-// (embed / LayerNorm / QKV GEMM / attention / FFN1 GEMM) - no separate conversion passes.
+//
+// fp32 mode: every tensor fp32, CUDA-core kernels, standalone LayerNorm launches - the in-GPU reference arithmetic.
+//
+// tc modes: GEMM operands travel as fp16 hi / lo planes written by the producing kernel's epilogue (embed / QKV GEMM /
+// attention / FFN1 GEMM / the two LayerNorm-site GEMMs) - no conversion passes - and there is NO LayerNorm kernel:
+// the attention-output and FFN-output projections write the raw pre-LayerNorm rows v (fp32 + planes) and their row
+// sums; the projections that consume LN(v) run on v with gamma folded into their weights and apply mean / rstd in the
+// epilogue; the residual of the next site is LN(v) recomputed from v and the sums (gemm_tc.cuh: TcLn).
+//   buffers: h / tc.h = the embedding output (layer 0) or v of the FFN-output site; a / tc.a = v of the attention-output
+//   site; stats2 / stats1 = their row sums.
 template <int VPL>
 int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
   const int Hd = H->d.hidden, I = H->d.intermediate;
   const bool tcm = H->gemm_mode != FD_GEMM_FP32_SIMT;
   launch_embed<VPL>(H, x, temb, temb_stride, tcm ? &H->tc.h : nullptr, st);
+  if (!tcm) {
+    for (int l = 0; l < H->d.layers; ++l) {
+      LayerW& w = H->layers[l];
+      int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, nullptr, w.b_qkv, nullptr, H->qkv, 3 * Hd, Hd, nullptr, nullptr, st);
+      if (rc) return rc;
+      launch_attention(H, w.dist, st);
+      rc = project(H, CAT_GEMM_OUT, fd::EPI_BIAS_RESID, H->ctx, w.w_o, nullptr, w.b_o, H->h, H->tmp, Hd, Hd, nullptr, nullptr, st);
+      if (rc) return rc;
+      launch_ln<VPL>(H, H->tmp, nullptr, w.ln1_g, w.ln1_b, H->a, nullptr, st);
+      rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, nullptr, w.b_i, nullptr, H->inter, I, Hd, nullptr, nullptr, st);
+      if (rc) return rc;
+      rc = project(H, CAT_GEMM_FFN2, fd::EPI_BIAS_RESID, H->inter, w.w_o2, nullptr, w.b_o2, H->a, H->tmp, Hd, I, nullptr, nullptr, st);
+      if (rc) return rc;
+      launch_ln<VPL>(H, H->tmp, nullptr, w.ln2_g, w.ln2_b, H->h, nullptr, st);
+    }
+    return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, nullptr, H->b_d1, nullptr, H->tmp, Hd, Hd, nullptr, nullptr, st);
+  }
+  const float inv_n = 1.0f / (float)Hd;
+  const int parts = H->stat_parts;
+  // FOLDINGDIFF_B200_RESID=planes (experiment): the residual source of a LayerNorm site is read back from the fp16
+  // hi / lo planes of the raw rows (22-bit) and no fp32 copy is written: 12 instead of 16 bytes per element and site
+  static const bool res_planes = [] { const char* e = getenv("FOLDINGDIFF_B200_RESID"); return e && e[0] == 'p'; }();
   for (int l = 0; l < H->d.layers; ++l) {
     LayerW& w = H->layers[l];
-    int rc = project(H, CAT_GEMM_QKV, fd::EPI_BIAS, H->h, w.w_qkv, &w.tq, tcm ? w.b_qkv_tc : w.b_qkv, nullptr, tcm ? nullptr : H->qkv,
-                     3 * Hd, Hd, &H->tc.h, tcm ? &H->tc.qkv : nullptr, st);
+    const LayerW* prev = l > 0 ? &H->layers[l - 1] : nullptr;
+    fd::TcLn in2;  // "the A rows are raw rows of the FFN-output site": layers > 0
+    if (prev) { in2.in_stats = H->stats2; in2.in_c = w.c_qkv; in2.in_parts = parts; in2.inv_n = inv_n; in2.eps = H->d.ln_eps; }
+    int rc = project(H, CAT_GEMM_QKV, prev ? fd::EPI_LNIN : fd::EPI_BIAS, nullptr, nullptr, &w.tq, w.d_qkv, nullptr, nullptr,
+                     3 * Hd, Hd, &H->tc.h, &H->tc.qkv, st, in2);
     if (rc) return rc;
-    if (tcm) { rc = launch_attention_mma(H, w, st); if (rc) return rc; }
-    else launch_attention(H, w.dist, st);
-    const bool fuse = tcm && fd::tc_gemm_ln_supported(&w.to, H->rows_pad);
-    if (fuse) {
-      rc = project_ln(H, CAT_GEMM_OUT, &H->tc.ctx, &w.to, w.b_o, H->h, w.ln1_g, w.ln1_b, H->a, &H->tc.a, Hd, st);
-      if (rc) return rc;
-    } else {
-      rc = project(H, CAT_GEMM_OUT, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->ctx, w.w_o, &w.to, w.b_o, H->h, H->tmp,
-                   Hd, Hd, &H->tc.ctx, nullptr, st);
-      if (rc) return rc;
-      launch_ln<VPL>(H, H->tmp, tcm ? H->h : nullptr, w.ln1_g, w.ln1_b, H->a, tcm ? &H->tc.a : nullptr, st);
-    }
-    rc = project(H, CAT_GEMM_FFN1, fd::EPI_BIAS_GELU, H->a, w.w_i, &w.ti, w.b_i, nullptr, tcm ? nullptr : H->inter,
-                 I, Hd, &H->tc.a, tcm ? &H->tc.inter : nullptr, st);
+    rc = launch_attention_mma(H, w, st);
     if (rc) return rc;
-    if (fuse) {
-      rc = project_ln(H, CAT_GEMM_FFN2, &H->tc.inter, &w.to2, w.b_o2, H->a, w.ln2_g, w.ln2_b, H->h, &H->tc.h, I, st);
-      if (rc) return rc;
-    } else {
-      rc = project(H, CAT_GEMM_FFN2, tcm ? fd::EPI_BIAS : fd::EPI_BIAS_RESID, H->inter, w.w_o2, &w.to2, w.b_o2, H->a,
-                   H->tmp, Hd, I, &H->tc.inter, nullptr, st);
-      if (rc) return rc;
-      launch_ln<VPL>(H, H->tmp, tcm ? H->a : nullptr, w.ln2_g, w.ln2_b, H->h, tcm ? &H->tc.h : nullptr, st);
-    }
+    fd::TcLn r1;  // attention-output site: residual = the layer input = embedding output (l = 0) or LN2 of layer l - 1
+    r1.res_v = res_planes ? nullptr : H->h; r1.res_hi = H->tc.h.hi; r1.res_lo = H->tc.h.lo;
+    r1.out_stats = H->stats1; r1.inv_n = inv_n; r1.eps = H->d.ln_eps;
+    if (prev) { r1.res_stats = H->stats2; r1.res_g = prev->ln2_g; r1.res_b = prev->ln2_b; r1.res_parts = parts; }
+    rc = project(H, CAT_GEMM_OUT, fd::EPI_LNRES, nullptr, nullptr, &w.to, w.b_o, nullptr, res_planes ? nullptr : H->a, Hd, Hd,
+                 &H->tc.ctx, &H->tc.a, st, r1);
+    if (rc) return rc;
+    fd::TcLn in1;
+    in1.in_stats = H->stats1; in1.in_c = w.c_i; in1.in_parts = parts; in1.inv_n = inv_n; in1.eps = H->d.ln_eps;
+    rc = project(H, CAT_GEMM_FFN1, fd::EPI_LNIN_GELU, nullptr, nullptr, &w.ti, w.d_i, nullptr, nullptr, I, Hd, &H->tc.a,
+                 &H->tc.inter, st, in1);
+    if (rc) return rc;
+    fd::TcLn r2;  // FFN-output site: residual = LN1 of this layer
+    r2.res_v = res_planes ? nullptr : H->a; r2.res_hi = H->tc.a.hi; r2.res_lo = H->tc.a.lo; r2.res_stats = H->stats1; r2.res_g = w.ln1_g; r2.res_b = w.ln1_b; r2.res_parts = parts;
+    r2.out_stats = H->stats2; r2.inv_n = inv_n; r2.eps = H->d.ln_eps;
+    rc = project(H, CAT_GEMM_FFN2, fd::EPI_LNRES, nullptr, nullptr, &w.to2, w.b_o2, nullptr, res_planes ? nullptr : H->h, Hd, I,
+                 &H->tc.inter, &H->tc.h, st, r2);
+    if (rc) return rc;
   }
-  return project(H, CAT_GEMM_HEAD, fd::EPI_BIAS_GELU, H->h, H->w_d1, &H->td1, H->b_d1, nullptr, H->tmp, Hd, Hd,
-                 &H->tc.h, nullptr, st);
+  fd::TcLn inh;
+  inh.in_stats = H->stats2; inh.in_c = H->c_d1; inh.in_parts = parts; inh.inv_n = inv_n; inh.eps = H->d.ln_eps;
+  return project(H, CAT_GEMM_HEAD, fd::EPI_LNIN_GELU, nullptr, nullptr, &H->td1, H->d_d1, nullptr, H->tmp, Hd, Hd, &H->tc.h,
+                 nullptr, st, inh);
 }
 
 int check_launch() {
@@ -410,21 +436,33 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
 #undef UP
   if (!rc) rc = upload(h, &h->time_table, time_table, (size_t)d.timesteps * H);
   h->coef.assign(coef, coef + (size_t)d.timesteps * 4);
-  // tensor-core operand planes of the weights (prepared once; cheap)
-  for (int l = 0; l < d.layers && !rc; ++l) {
-    LayerW& w = h->layers[l];
-    // the query rows of the fused QKV weight (and their bias) also carry the de-bias of the attention kernel's
-    // K = 32 products (gemm_tc.cuh: tc_split_weight_kernel)
-    if (fd::tc_pack_weight(w.w_qkv, 3 * H, H, &w.tq, H) || fd::tc_pack_weight(w.w_o, H, H, &w.to) ||
-        fd::tc_pack_weight(w.w_i, I, H, &w.ti) || fd::tc_pack_weight(w.w_o2, H, I, &w.to2))
-      rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (!rc) rc = dev_alloc(h, (void**)&w.b_qkv_tc, sizeof(float) * 3 * H);
-    if (!rc) {
-      const fd::TcRz rz = fd::tc_rz();
-      fd::tc_scale_qbias_kernel<<<(3 * H + 255) / 256, 256>>>(w.b_qkv, w.b_qkv_tc, 3 * H, H, rz.alpha, rz.beta_att);
+  // tensor-core operand planes of the weights (prepared once; cheap).  The projections that consume a LayerNorm
+  // output carry its gamma in their K columns and its mean / beta terms in the epilogue vectors c / d (gemm_tc.cuh:
+  // TcLn); the query rows of the fused QKV weight also carry the de-bias of the attention kernel's K = 32 products.
+  {
+    const fd::TcRz rz = fd::tc_rz();
+    auto fold = [&](const float* w_dev, const float* b_dev, const float* g, const float* be, int n, int k, int q_rows,
+                    float** c_out, float** d_out) -> int {
+      int r = dev_alloc(h, (void**)c_out, sizeof(float) * n);
+      if (!r) r = dev_alloc(h, (void**)d_out, sizeof(float) * n);
+      if (r) return r;
+      fd::tc_fold_vectors_kernel<<<(n * 32 + 255) / 256, 256>>>(w_dev, b_dev, g, be, n, k, q_rows, rz.alpha, rz.beta_att, *c_out, *d_out);
+      return FD_OK;
+    };
+    for (int l = 0; l < d.layers && !rc; ++l) {
+      LayerW& w = h->layers[l];
+      const float* g_in = l > 0 ? h->layers[l - 1].ln2_g : nullptr;  // LayerNorm whose output this layer's QKV reads
+      const float* b_in = l > 0 ? h->layers[l - 1].ln2_b : nullptr;
+      if (fd::tc_pack_weight(w.w_qkv, 3 * H, H, &w.tq, H, g_in) || fd::tc_pack_weight(w.w_o, H, H, &w.to) ||
+          fd::tc_pack_weight(w.w_i, I, H, &w.ti, 0, w.ln1_g) || fd::tc_pack_weight(w.w_o2, H, I, &w.to2))
+        rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (!rc) rc = fold(w.w_qkv, w.b_qkv, g_in, b_in, 3 * H, H, H, &w.c_qkv, &w.d_qkv);
+      if (!rc) rc = fold(w.w_i, w.b_i, w.ln1_g, w.ln1_b, I, H, 0, &w.c_i, &w.d_i);
     }
+    const LayerW& last = h->layers[d.layers - 1];
+    if (!rc && fd::tc_pack_weight(h->w_d1, H, H, &h->td1, 0, last.ln2_g)) rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed");
+    if (!rc) rc = fold(h->w_d1, h->b_d1, last.ln2_g, last.ln2_b, H, H, 0, &h->c_d1, &h->d_d1);
   }
-  if (!rc && fd::tc_pack_weight(h->w_d1, H, H, &h->td1)) rc = fail(FD_ERR_CUDA, "tensor-core weight packing failed");
   // distance embeddings as fp16 hi / lo planes, padded to 256 rows (row 2*max_pos-1.. are zero)
   for (int l = 0; l < d.layers && !rc; ++l) {
     LayerW& w = h->layers[l];
@@ -537,6 +575,11 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     FD_CUDA(cudaMalloc(&h->a, sizeof(float) * r * Hd));
     FD_CUDA(cudaMalloc(&h->inter, sizeof(float) * r * I));
     if (fd::tc_alloc_acts(&h->tc, rows_pad, Hd, I)) return fail(FD_ERR_CUDA, "tensor-core workspace allocation failed");
+    h->stat_parts = 2 * Hd / fd::tc_pick_bn(Hd);
+    FD_CUDA(cudaMalloc(&h->stats1, sizeof(float2) * r * h->stat_parts));
+    FD_CUDA(cudaMalloc(&h->stats2, sizeof(float2) * r * h->stat_parts));
+    FD_CUDA(cudaMemsetAsync(h->stats1, 0, sizeof(float2) * r * h->stat_parts, st));
+    FD_CUDA(cudaMemsetAsync(h->stats2, 0, sizeof(float2) * r * h->stat_parts, st));
     if (fd::attp_make_map(&h->att_hi, h->tc.qkv.hi, rows_pad, 3 * Hd) || fd::attp_make_map(&h->att_lo, h->tc.qkv.lo, rows_pad, 3 * Hd))
       return fail(FD_ERR_CUDA, "attention tensor map creation failed");
     h->cap_batch = batch; h->cap_rows = rows_pad; h->cap_bn = batch * n_pad;

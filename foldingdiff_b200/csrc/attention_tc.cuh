@@ -23,10 +23,17 @@
 //
 // Warp roles (384 threads, one persistent CTA per SM):  warps 0..3 and 4..7 = two softmax warpgroups that take
 // alternate items, warp 8 = TMA producer, warp 9 = S / R MMA issuer + TMEM owner, warp 10 = P V MMA issuer (warp 11
-// only pads the producer warpgroup so that setmaxnreg can move its registers to the softmax threads).  TMEM (512 columns):
-// S [0,128) | R [128,384) | P hi [384,416) lo [416,448) (64 keys per round) | O [448,480).  S and R are single
-// buffered: a warpgroup releases them as soon as its rows sit in registers (sr_empty), so the S/R MMAs of
-// item i+1 run under the softmax of item i, and P V of item i runs under the S/R load of item i+1.
+// only pads the producer warpgroup so that setmaxnreg can move its registers to the softmax threads).
+//
+// TMEM (512 columns), round-2 layout: every warpgroup owns a 128-column region, the relative-key product is shared -
+//     warpgroup w:  [128 w, 128 w + 128)   S [0, nk32)  ->  P round 0 (keys 0..63) hi [0, 32) lo [32, 64) | O [64, 96) |
+//                                          P round 1 hi / lo: [96, 112) / [112, 128) if nk32 <= 96, else [0, 32) / [32, 64)
+//     R:            [256, 512)
+// S is read into registers before anything else is written to the region, so P and O reuse its columns.  Round 1 only
+// has to wait for round 0's P V when the chain has more than 96 keys, and by then its exponentials have been computed
+// under that very product.  (Round-1 layout: ONE 64-column P buffer and one O for both warpgroups; ncu showed 39 % of the
+// softmax warps' samples in the three waits of that hand-off - profiles/r01_attention_tc_analysis.md.)  The price: S of
+// item i + 2 cannot be issued before O of item i has been read (R of the next item still can: it is issued first).
 //
 // Every mbarrier wait is bounded (mbar_wait): a broken pipeline sets the error flag and ends the kernel.
 #pragma once
@@ -39,7 +46,7 @@ constexpr int ATC_PLANE_BYTES = 128 * 64;            // 128 rows x 32 halves, 64
 constexpr int ATC_SLOT_BYTES = 6 * ATC_PLANE_BYTES;  // Q hi, Q lo, K hi, K lo, V hi, V lo
 constexpr int ATC_SCR_PITCH = 68;                    // words per thread-private skew row (== 4 mod 32)
 constexpr int ATC_THREADS = 384;  // warpgroups: 0 and 1 = softmax, 2 = producers (warp 8 TMA, warp 9 MMA)
-constexpr uint32_t ATC_COL_S = 0, ATC_COL_R = 128, ATC_COL_P = 384, ATC_COL_O = 448;
+constexpr uint32_t ATC_COL_WG = 128, ATC_COL_R = 256, ATC_COL_O = 64, ATC_COL_P1 = 96;  // see the TMEM layout above
 constexpr int ATC_DBG_ROW = 128 + 128 + 32 + 2;      // floats per row of the debug dump
 
 constexpr size_t atc_smem_bytes() {
@@ -188,30 +195,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   // A barrier a warpgroup WAITS on must show it every phase: a waiter that only looks at every other phase cannot
   // tell "two phases behind" from "done" by parity (warpgroup 1 would sail through its very first wait).  So the
   // MMA -> softmax barriers exist once per warpgroup; the softmax -> MMA ones are seen in item order by the MMA warp.
-  uint64_t* sr_full = bars + 2 * ATC_SLOTS;  // [2] MMA -> softmax warpgroup (it & 1)
-  uint64_t* o_full = sr_full + 2;            // [2] MMA -> softmax warpgroup (it & 1)
-  uint64_t* sr_empty = sr_full + 4;          // softmax -> MMA
-  uint64_t* o_empty = sr_full + 5;           // softmax -> MMA
-  uint64_t* p_full = sr_full + 6;            // [2] softmax -> MMA, per 64-key round
-  uint64_t* p_empty = sr_full + 8;           // [2] MMA -> softmax, per round (see the waits for why parity is exact)
-  uint64_t* s_empty = sr_full + 10;          // softmax -> MMA: S sits in registers (R is released later, by sr_empty)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 11);
+  uint64_t* sr_full = bars + 2 * ATC_SLOTS;  // [2] MMA -> softmax warpgroup (it & 1): its S and the shared R are complete
+  uint64_t* o_full = sr_full + 2;            // [2] MMA -> softmax warpgroup: O complete
+  uint64_t* p0_done = sr_full + 4;           // [2] MMA -> softmax warpgroup: round-0 P V retired (its P columns may be rewritten)
+  uint64_t* reg_empty = sr_full + 6;         // [2] softmax warpgroup -> MMA: O has been read, the region is free for the next S
+  uint64_t* p_full = sr_full + 8;            // [2][2] softmax warpgroup -> MMA, per 64-key round: index 2 w + r
+  uint64_t* r_empty = sr_full + 12;          // softmax -> MMA: the skew has consumed R
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_full + 13);
   // Item descriptors {r0, n_rows, n_keys, head, chain}: the TMA warp, three items ahead of everyone, is the only role
   // that reads them from global memory; it parks them in an 8-entry shared ring BEFORE arming the item's kv_full
   // barrier, so every later role reads them with one LDS after a barrier it waits on anyway.  (ncu: with each role
   // prefetching its own copy the compiler spilled the in-flight registers and stalled at the spill - ISETP / IMAD /
   // BRA / STL long-scoreboard stalls were a quarter of the softmax warps' busy samples.)  An entry is rewritten 8
   // items later, after kv_empty of item it + 5: both warpgroups have left item `it` by then.
-  int* meta = reinterpret_cast<int*>(bars) + 48;  // byte 192 of the 512-byte barrier block (barriers + TMEM slot end at 140)
+  int* meta = reinterpret_cast<int*>(bars) + 48;  // byte 192 of the 512-byte barrier block (barriers + TMEM slot end at 156)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_it = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
 
   if (tid == 0) {
     for (int i = 0; i < ATC_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
-    mbar_init(sr_empty, 4); mbar_init(o_empty, 4); mbar_init(s_empty, 4);
+    mbar_init(r_empty, 4);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+      mbar_init(&sr_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&p0_done[i], 1); mbar_init(&reg_empty[i], 4);
+      mbar_init(&p_full[2 * i], 4); mbar_init(&p_full[2 * i + 1], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo);
@@ -233,8 +240,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   pdl_wait();  // the prologue (barriers, TMEM, the layer's distance table: weights) ran under the QKV GEMM's tail
   // shared-space addresses of the barriers (8 bytes each, same order as above)
   const uint32_t b_kv_full = smem_u32(kv_full), b_kv_empty = smem_u32(kv_empty), b_sr_full = smem_u32(sr_full);
-  const uint32_t b_o_full = smem_u32(o_full), b_sr_empty = smem_u32(sr_empty), b_o_empty = smem_u32(o_empty);
-  const uint32_t b_p_full = smem_u32(p_full), b_p_empty = smem_u32(p_empty), b_s_empty = smem_u32(s_empty);
+  const uint32_t b_o_full = smem_u32(o_full), b_p0_done = smem_u32(p0_done), b_reg_empty = smem_u32(reg_empty);
+  const uint32_t b_p_full = smem_u32(p_full), b_r_empty = smem_u32(r_empty);
   const uint32_t meta_s = smem_u32(meta);
   auto meta_item = [&](int it) {  // valid once a barrier downstream of kv_full(it) has been waited for
     const uint32_t m = meta_s + 32u * (uint32_t)(it & (ATC_META_RING - 1));
@@ -279,36 +286,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       const uint32_t e_hi_s = smem_u32(Es_hi), e_lo_s = smem_u32(Es_lo);
       // item descriptors one iteration ahead: their (dependent) global loads stay off the issue path
       for (int it = 0; it < n_it; ++it) {
-        {  // ---- S and R of item `it`
-          const int slot = it % ATC_SLOTS;
+        {  // ---- R (shared region) and S (the warpgroup's region) of item `it`
+          const int slot = it % ATC_SLOTS, w = it & 1, j = it >> 1;
           if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((it / ATC_SLOTS) & 1))) { atomicExch(err_flag, 302); break; }
           const AtcItem a = meta_item(it);
           const int nk32 = a.nk32(), nr32 = a.nr32();
-          if (!atc_wait(b_s_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 309); break; }
-          tc_fence_after();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t q_hi = s0, q_lo = s0 + ATC_PLANE_BYTES, k_hi = s0 + 2 * ATC_PLANE_BYTES, k_lo = s0 + 3 * ATC_PLANE_BYTES;
           const uint32_t id_s = umma_idesc_f16(nk32), id_r = umma_idesc_f16(nk32 + nr32);
           const uint32_t e_off = (uint32_t)(128 - nk32) * 64u;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t ko = ks * 32;  // bytes inside the 64-byte swizzle row
-            const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
-            umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, ks);
-            umma_f16(tmem + ATC_COL_S, dq_hi, atc_desc(k_lo + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
-            umma_f16(tmem + ATC_COL_S, dq_lo, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
-          }
-          if (!atc_wait(b_sr_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 303); break; }
+          // R first: its region frees early (after the previous item's skew), the S region only after that warpgroup's
+          // previous item has read its O
+          if (!atc_wait(b_r_empty, (uint32_t)((it & 1) ^ 1))) { atomicExch(err_flag, 303); break; }
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t ko = ks * 32;
+            const uint32_t ko = ks * 32;  // bytes inside the 64-byte swizzle row
             const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
             umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, ks);
             umma_f16(tmem + ATC_COL_R, dq_hi, atc_desc(e_lo_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
             umma_f16(tmem + ATC_COL_R, dq_lo, atc_desc(e_hi_s + e_off + ko, dsc.k_lbo, dsc.k_hi32), id_r, 1u);
           }
-          atc_commit(b_sr_full + 8 * (it & 1));
+          if (!atc_wait(b_reg_empty + 8 * w, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 309); break; }
+          tc_fence_after();
+          const uint32_t t_s = tmem + ATC_COL_WG * (uint32_t)w;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ko = ks * 32;
+            const uint64_t dq_hi = atc_desc(q_hi + ko, dsc.k_lbo, dsc.k_hi32), dq_lo = atc_desc(q_lo + ko, dsc.k_lbo, dsc.k_hi32);
+            umma_f16(t_s, dq_hi, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, ks);
+            umma_f16(t_s, dq_hi, atc_desc(k_lo + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
+            umma_f16(t_s, dq_lo, atc_desc(k_hi + ko, dsc.k_lbo, dsc.k_hi32), id_s, 1u);
+          }
+          atc_commit(b_sr_full + 8 * w);
           atc_commit(b_kv_empty + 8 * slot);  // this thread's half of the slot release (Q / K reads retired)
         }
       }
@@ -321,27 +331,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     if (lane == 0) {
       bool ok = true;
       for (int j = 0; j < n_it && ok; ++j) {
-        {  // ---- O = P V of item j, 64 keys per round
-          const int slot = j % ATC_SLOTS;
+        {  // ---- O = P V of item j, 64 keys per round, inside the item's warpgroup region
+          const int slot = j % ATC_SLOTS, w = j & 1;
+          const uint32_t wpar = (uint32_t)((j >> 1) & 1);
           if (!atc_wait(b_kv_full + 8 * slot, (uint32_t)((j / ATC_SLOTS) & 1))) { atomicExch(err_flag, 310); break; }
           const int nk32 = meta_item(j).nk32();
           const uint32_t s0 = smem_u32(ring + (size_t)slot * ATC_SLOT_BYTES);
           const uint32_t v_hi = s0 + 4 * ATC_PLANE_BYTES, v_lo = s0 + 5 * ATC_PLANE_BYTES;
-          if (!atc_wait(b_o_empty, (uint32_t)((j & 1) ^ 1))) { atomicExch(err_flag, 304); break; }
+          const uint32_t t_w = tmem + ATC_COL_WG * (uint32_t)w, t_o = t_w + ATC_COL_O;
           for (int r = 0; r < 2 && ok; ++r) {
-            if (!atc_wait(b_p_full + 8 * r, (uint32_t)(j & 1))) { atomicExch(err_flag, 305); ok = false; break; }
+            if (!atc_wait(b_p_full + 8 * (2 * w + r), wpar)) { atomicExch(err_flag, 305); ok = false; break; }
             tc_fence_after();
             const int nks = min(4, (nk32 - 64 * r) >> 4);
+            // round 1 of a chain of at most 96 keys has its own 32 columns; otherwise the rounds share [0, 64)
+            const bool own = r == 1 && nk32 <= 96;
+            const uint32_t p_hi0 = t_w + (own ? ATC_COL_P1 : 0u), lo_off = own ? 16u : 32u;
             for (int ks = 0; ks < nks; ++ks) {
               const uint32_t vb = (uint32_t)(64 * r + 16 * ks) * 64u;
-              const uint32_t p_hi = tmem + ATC_COL_P + 8 * ks, p_lo = tmem + ATC_COL_P + 32 + 8 * ks;
-              umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
-              umma_f16_ts(tmem + ATC_COL_O, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
-              umma_f16_ts(tmem + ATC_COL_O, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+              const uint32_t p_hi = p_hi0 + 8 * ks, p_lo = p_hi + lo_off;
+              umma_f16_ts(t_o, p_hi, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, (r | ks) != 0 ? 1u : 0u);
+              umma_f16_ts(t_o, p_lo, atc_desc(v_hi + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
+              umma_f16_ts(t_o, p_hi, atc_desc(v_lo + vb, dsc.v_lbo, dsc.v_hi32), dsc.pv_idesc, 1u);
             }
-            atc_commit(b_p_empty + 8 * r);
+            if (r == 0) atc_commit(b_p0_done + 8 * w);
           }
-          atc_commit(b_o_full + 8 * (j & 1));
+          atc_commit(b_o_full + 8 * w);
           atc_commit(b_kv_empty + 8 * slot);  // the other half of the slot release (V reads retired)
         }
       }
@@ -353,6 +367,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const int wg = warp >> 2, quad = warp & 3;  // TMEM lanes [32 quad, 32 quad + 32) are this warp's
     const int row = quad * 32 + lane;                 // query row == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_reg = t_lane + ATC_COL_WG * (uint32_t)wg;  // this warpgroup's S / P / O region
     float* srow = scr + (size_t)row * ATC_SCR_PITCH;
     const float c_scale = 0.17677669529663688110f * 1.44269504088896340736f;  // log2(e) / sqrt(32)
     // descriptor fields are re-read from the shared ring wherever they are used (an LDS each) instead of being kept
@@ -360,7 +375,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     auto fld = [&](int it, int k) { return (int)lds_u32a(meta_s + 32u * (uint32_t)(it & (ATC_META_RING - 1)) + 4u * (uint32_t)k); };
 #define ATC_ACTIVE(it) (quad * 32 < fld(it, 1))
     for (int it = wg; it < (int)lds_u32a(meta_s + 32u * ATC_META_RING); it += 2) {  // n_it, parked behind the ring
-      const uint32_t par = (uint32_t)(it & 1), wpar = (uint32_t)((it >> 1) & 1);  // item parity, per-warpgroup parity
+      const uint32_t wpar = (uint32_t)((it >> 1) & 1);  // per-warpgroup phase parity
       uint32_t su[128];
       if (!atc_wait(b_sr_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 306); break; }
       tc_fence_after();
@@ -372,12 +387,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       if (ATC_ACTIVE(it)) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c * 32 < nk32) tmem_ld32_issue(t_lane + ATC_COL_S + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
+          if (c * 32 < nk32) tmem_ld32_issue(t_reg + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&su[32 * c]));
         tmem_ld_wait();
       }
-      tc_fence_before();  // S is in registers: the next item's Q K^T may overwrite it while this one's skew reads R
-      __syncwarp();
-      if (lane == 0) atc_arrive(b_s_empty);
       if (ATC_ACTIVE(it)) {
         if (DBG && drow) {
 #pragma unroll
@@ -411,7 +423,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       }
       tc_fence_before();  // every TMEM read of S / R by this warp has completed (tcgen05.wait::ld above)
       __syncwarp();
-      if (lane == 0) atc_arrive(b_sr_empty);
+      if (lane == 0) atc_arrive(b_r_empty);  // R may be overwritten by the next item's Q E^T (S stays this warpgroup's)
 
       // ---- mask, row max on the raw logits, p = 2^((s - max) * log2e / sqrt(32)), row sum
       if (ATC_ACTIVE(it)) {
@@ -446,38 +458,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
           }
         }
         m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        const float neg = -m * c_scale;
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 32 < nk32) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int k = 32 * c + i;
-              const float p0 = ex2_approx(fmaf(__uint_as_float(su[k]), c_scale, neg));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(su[k + 1]), c_scale, neg));
-              const float p2 = ex2_approx(fmaf(__uint_as_float(su[k + 2]), c_scale, neg));
-              const float p3 = ex2_approx(fmaf(__uint_as_float(su[k + 3]), c_scale, neg));
-              su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
-              su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
-              s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-            }
-          }
-        }
-        sum = (s0 + s1) + (s2 + s3);
-        m *= c_scale;  // (debug dump: row max in log2 units)
       }
-      // ---- P as fp16 hi / lo planes into TMEM, 64 keys per round
+      // ---- per 64-key round: p = 2^((s - max) * log2e / sqrt(32)), row sum, P as fp16 hi / lo planes into TMEM.
+      // The exponentials of round 1 are computed AFTER round 0 has been handed to the tensor core, so they run under
+      // its P V products (ncu, round 1: the wait for p_empty[0] behind a finished softmax was 11 % of all samples).
+      const float neg = -m * c_scale;
+      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
       bool ok = true;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        // round 0 reuses the buffer the previous item's round 1 read; round 1 the one this item's round 0 read.
-        // Both barriers are shared by the two warpgroups; the parity test is still exact: phase it - 2 of
-        // p_empty[1] retired before this warpgroup's own o_full of item it - 2, and phase it - 1 of p_empty[0]
-        // retires (commit order) before phase it - 1 of p_empty[1], which was just waited for.
-        if (!atc_wait(b_p_empty + 8 * (r ^ 1), r == 0 ? (par ^ 1u) : par)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
-        tc_fence_after();
-        if (ATC_ACTIVE(it) && 64 * r < nk32) {
+        const bool live = ATC_ACTIVE(it) && 64 * r < nk32;
+        if (live) {
+#pragma unroll
+          for (int c = 2 * r; c < 2 * r + 2; ++c) {
+            if (c * 32 < nk32) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const int k = 32 * c + i;
+                const float p0 = ex2_approx(fmaf(__uint_as_float(su[k]), c_scale, neg));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(su[k + 1]), c_scale, neg));
+                const float p2 = ex2_approx(fmaf(__uint_as_float(su[k + 2]), c_scale, neg));
+                const float p3 = ex2_approx(fmaf(__uint_as_float(su[k + 3]), c_scale, neg));
+                su[k] = __float_as_uint(p0); su[k + 1] = __float_as_uint(p1);
+                su[k + 2] = __float_as_uint(p2); su[k + 3] = __float_as_uint(p3);
+                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+              }
+            }
+          }
+        }
+        // round 0 overwrites S (already in registers); round 1 has its own columns unless the chain has more than 96
+        // keys - then it reuses round 0's once that P V has retired (its exponentials were computed under it)
+        const bool own = r == 1 && nk32 <= 96;
+        if (r == 1 && nk32 > 96) {
+          if (!atc_wait(b_p0_done + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 307); ok = false; break; }
+          tc_fence_after();
+        }
+        if (live) {
+          const uint32_t t_p = t_reg + (own ? ATC_COL_P1 : 0u), lo_off = own ? 16u : 32u;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {  // 32 keys -> 16 packed columns per plane
             if (64 * r + 32 * g < nk32) {
@@ -491,26 +508,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
               for (int q = 0; q < 16; ++q)
                 split2s(__uint_as_float(su[64 * r + 32 * g + 2 * q]), __uint_as_float(su[64 * r + 32 * g + 2 * q + 1]),
                         q < 8 ? sc0 : sc1, ph[q], pl[q]);
-              tmem_st16(t_lane + ATC_COL_P + 16 * g, ph);
-              tmem_st16(t_lane + ATC_COL_P + 32 + 16 * g, pl);
+              tmem_st16(t_p + 16 * g, ph);
+              tmem_st16(t_p + lo_off + 16 * g, pl);
             }
           }
           tmem_st_wait();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) atc_arrive(b_p_full + 8 * r);
+        if (lane == 0) atc_arrive(b_p_full + 8 * (2 * wg + r));
       }
+      sum = (s0 + s1) + (s2 + s3);
+      m *= c_scale;  // (debug dump: row max in log2 units)
       if (!ok) break;
       // ---- O: normalise and store ctx as hi / lo planes
       if (!atc_wait(b_o_full + 8 * wg, wpar)) { if (lane == 0) atomicExch(err_flag, 308); break; }
       tc_fence_after();
       uint32_t o[32];
       const bool active = ATC_ACTIVE(it);
-      if (active) tmem_ld32(t_lane + ATC_COL_O, o);
+      if (active) tmem_ld32(t_reg + ATC_COL_O, o);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) atc_arrive(b_o_empty);
+      if (lane == 0) atc_arrive(b_reg_empty + 8 * wg);  // the region is free: the S product of this warpgroup's next item may land
       if (active && row < fld(it, 1)) {
         const float inv = 1.0f / sum;
         if (DBG && drow) {

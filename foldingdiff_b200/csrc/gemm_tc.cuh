@@ -60,6 +60,34 @@ struct TcActs {
   TcPlane h, qkv, ctx, a, inter;
 };
 
+// LayerNorm folded into the projections (EPI_LNIN*, EPI_LNRES).  BertSelfOutput / BertOutput compute
+//     y = LN(v) = (v - m) * r * gamma + beta,   v = dense(x) + residual,   m / r = the row's mean / 1 / sqrt(var + eps)
+// and the next projection computes  y W^T + b.  Since  y W^T + b = r * (v W'^T - m * c) + d  with the STATIC
+//     W' = W diag(gamma),   c[n] = sum_k gamma[k] W[n, k],   d[n] = sum_k beta[k] W[n, k] + b[n],
+// the consuming GEMM can take the RAW rows v as its A operand (hi / lo planes written by the producing GEMM's
+// epilogue) and apply the normalisation as a per-row affine map in its own epilogue.  The standalone LayerNorm
+// launches (24 per reverse step, 16 bytes of HBM traffic per element each) disappear:
+//   producer (EPI_LNRES)   v = acc * s + bias + residual;  writes v (fp32, the later residual source), its hi / lo
+//                          planes, and per-row partial sums (sum v, sum v^2) of its column range - one slot per
+//                          (column block, epilogue column group), summed by the readers in slot order (deterministic).
+//                          The residual is either a plain fp32 tensor (layer 0: the embedding output) or the
+//                          normalised value of the PREVIOUS site, recomputed on the fly from that site's v and sums.
+//   consumer (EPI_LNIN*)   y = r * (acc * s - m * c[n]) + d[n]   (+ GELU)
+struct TcLn {
+  const float2* in_stats = nullptr;   // consumer: [rows][in_parts] partial (sum, sum of squares) of the A rows
+  const float* in_c = nullptr;        //           c[n]  (d[n] travels as `bias`)
+  int in_parts = 0;
+  const __half* res_hi = nullptr;     // producer: residual source rows as fp16 hi / lo planes (used when res_v is null)
+  const __half* res_lo = nullptr;
+  const float* res_v = nullptr;       // producer: residual source rows (fp32) ...
+  const float2* res_stats = nullptr;  //           ... normalised with these sums (nullptr: used as they are)
+  const float* res_g = nullptr;
+  const float* res_b = nullptr;
+  int res_parts = 0;
+  float2* out_stats = nullptr;        // producer: [rows][2 N / BN]
+  float inv_n = 0.0f, eps = 0.0f;     // 1 / hidden, LayerNorm epsilon
+};
+
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
@@ -261,13 +289,23 @@ struct TcCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 };
 
+// four consecutive residual-source values: fp32 rows, or their fp16 hi + lo planes
+__device__ __forceinline__ float4 tc_load_res4(const TcLn& ln, const float* plain, size_t off) {
+  if (plain) return *reinterpret_cast<const float4*>(plain + off);
+  if (ln.res_v) return *reinterpret_cast<const float4*>(ln.res_v + off);
+  const uint2 a = *reinterpret_cast<const uint2*>(ln.res_hi + off), b = *reinterpret_cast<const uint2*>(ln.res_lo + off);
+  const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a23 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+  const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b23 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+  return make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+}
+
 template <int BN, int NPASS, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const float* __restrict__ bias, const float* __restrict__ resid, float* __restrict__ C,
                __half* __restrict__ c_hi, __half* __restrict__ c_lo, int M, int N, int K,
-               float out_scale, int* __restrict__ err_flag, unsigned long long a_policy) {
+               float out_scale, int* __restrict__ err_flag, unsigned long long a_policy, TcLn ln) {
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
   using Cfg = TcCfg<BN, NPASS, PAIR>;
   pdl_trigger();
@@ -407,14 +445,67 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;
     float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 32 * EP;
     const int lr = lane >> 3, lc = (lane & 7) * 4;  // coalesced layout: row inside a 4-row group, first column
+    constexpr bool LNIN = EPI == EPI_LNIN || EPI == EPI_LNIN_GELU;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const int m0 = ((tile / n_blocks) * CL + crank) * TC_BM, n0 = (tile % n_blocks) * BN;
+      const int row0 = m0 + quad * 32 + lr;  // this thread's rows: row0 + 4 i, i = 0..7
+      // per-row LayerNorm statistics, fetched before the accumulator is waited for (independent of it)
+      float mu[8], rs_[8];      // consumer: mean / rstd of the A rows;  producer: of the residual source rows
+      float s1[8], s2[8];       // producer: partial sums of this thread's output columns
+      if (LNIN || (EPI == EPI_LNRES && ln.res_stats)) {
+        const float2* st = LNIN ? ln.in_stats : ln.res_stats;
+        const int parts = LNIN ? ln.in_parts : ln.res_parts;
+        // all loads of the 8 rows are issued before the first use (a loop that accumulates as it loads is a chain of
+        // dependent L2 round trips: measured 13 us per tile); 2 or 4 partials per row = one or two 16-byte loads
+        float a1[8], a2[8];
+        if (parts == 4) {
+          float4 u[8], w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4* q = reinterpret_cast<const float4*>(st + (size_t)(row0 + 4 * i) * 4);
+            u[i] = q[0]; w[i] = q[1];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a1[i] = ((u[i].x + u[i].z) + w[i].x) + w[i].z; a2[i] = ((u[i].y + u[i].w) + w[i].y) + w[i].w; }
+        } else if (parts == 2) {
+          float4 u[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const float4*>(st + (size_t)(row0 + 4 * i) * 2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a1[i] = u[i].x + u[i].z; a2[i] = u[i].y + u[i].w; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            a1[i] = 0.0f; a2[i] = 0.0f;
+            for (int p = 0; p < parts; ++p) {
+              const float2 v2 = st[(size_t)(row0 + 4 * i) * parts + p];
+              a1[i] += v2.x; a2[i] += v2.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float mean = a1[i] * ln.inv_n;
+          mu[i] = mean;
+          rs_[i] = 1.0f / sqrtf(fmaxf(fmaf(-mean, mean, a2[i] * ln.inv_n), 0.0f) + ln.eps);
+        }
+      }
+      if (EPI == EPI_LNRES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+      }
       if (!mbar_wait(&acc_full[acc], acc_phase)) { if (lane == 0) atomicExch(err_flag, 104); break; }
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       uint32_t v[32];
       tmem_ld32_issue(t_row + (uint32_t)col_lo, v);
+      float4 rs[8];  // residual rows of the chunk being processed (issued one chunk ahead)
+      if (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rs[i] = tc_load_res4(ln, EPI == EPI_LNRES ? nullptr : resid, (size_t)(row0 + 4 * i) * N + n0 + col_lo + lc);
+      }
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c0 = col_lo + ci * 32;
@@ -431,21 +522,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           else mbar_arrive(&acc_empty[acc]);
         }
         const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + lc);
-        float4 rs[8];
-        if (EPI == EPI_BIAS_RESID) {
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = c4, e4 = c4;
+        if (LNIN) c4 = *reinterpret_cast<const float4*>(ln.in_c + n0 + c0 + lc);
+        if (EPI == EPI_LNRES && ln.res_stats) {
+          g4 = *reinterpret_cast<const float4*>(ln.res_g + n0 + c0 + lc);
+          e4 = *reinterpret_cast<const float4*>(ln.res_b + n0 + c0 + lc);
+        }
+        float4 rcur[8];
+        if (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            rs[i] = *reinterpret_cast<const float4*>(resid + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + n0 + c0 + lc);
+          for (int i = 0; i < 8; ++i) rcur[i] = rs[i];
+          if (ci + 1 < NCH) {  // the next chunk's residual rows travel under this chunk's math and stores
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              rs[i] = tc_load_res4(ln, EPI == EPI_LNRES ? nullptr : resid, (size_t)(row0 + 4 * i) * N + n0 + c0 + 32 + lc);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + lr;
           const float4 a = *reinterpret_cast<const float4*>(stg + r * EP + lc);
           const size_t off = (size_t)(m0 + quad * 32 + r) * N + n0 + c0 + lc;
-          float o0 = fmaf(a.x, out_scale, b4.x), o1 = fmaf(a.y, out_scale, b4.y);
-          float o2 = fmaf(a.z, out_scale, b4.z), o3 = fmaf(a.w, out_scale, b4.w);
-          if (EPI == EPI_BIAS_RESID) { o0 += rs[i].x; o1 += rs[i].y; o2 += rs[i].z; o3 += rs[i].w; }
-          if (EPI == EPI_BIAS_GELU) { o0 = gelu_erf_fast(o0); o1 = gelu_erf_fast(o1); o2 = gelu_erf_fast(o2); o3 = gelu_erf_fast(o3); }
+          float o0, o1, o2, o3;
+          if (LNIN) {  // y = rstd * (acc * s - mean * c[n]) + d[n]
+            o0 = fmaf(rs_[i], fmaf(-mu[i], c4.x, a.x * out_scale), b4.x); o1 = fmaf(rs_[i], fmaf(-mu[i], c4.y, a.y * out_scale), b4.y);
+            o2 = fmaf(rs_[i], fmaf(-mu[i], c4.z, a.z * out_scale), b4.z); o3 = fmaf(rs_[i], fmaf(-mu[i], c4.w, a.w * out_scale), b4.w);
+          } else {
+            o0 = fmaf(a.x, out_scale, b4.x); o1 = fmaf(a.y, out_scale, b4.y);
+            o2 = fmaf(a.z, out_scale, b4.z); o3 = fmaf(a.w, out_scale, b4.w);
+          }
+          if (EPI == EPI_BIAS_RESID) { o0 += rcur[i].x; o1 += rcur[i].y; o2 += rcur[i].z; o3 += rcur[i].w; }
+          if (EPI == EPI_LNRES) {
+            float4 rr = rcur[i];
+            if (ln.res_stats) {  // the previous site's LayerNorm output, recomputed from its raw rows
+              rr.x = ((rr.x - mu[i]) * rs_[i]) * g4.x + e4.x; rr.y = ((rr.y - mu[i]) * rs_[i]) * g4.y + e4.y;
+              rr.z = ((rr.z - mu[i]) * rs_[i]) * g4.z + e4.z; rr.w = ((rr.w - mu[i]) * rs_[i]) * g4.w + e4.w;
+            }
+            o0 += rr.x; o1 += rr.y; o2 += rr.z; o3 += rr.w;
+            s1[i] += (o0 + o1) + (o2 + o3);
+            s2[i] = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, s2[i]))));
+          }
+          if (EPI == EPI_BIAS_GELU || EPI == EPI_LNIN_GELU) { o0 = gelu_erf_fast(o0); o1 = gelu_erf_fast(o1); o2 = gelu_erf_fast(o2); o3 = gelu_erf_fast(o3); }
           if (C) *reinterpret_cast<float4*>(C + off) = make_float4(o0, o1, o2, o3);
           if (c_hi) {
             const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
@@ -463,6 +580,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         __syncwarp();  // staging buffer is free for the next chunk
       }
+      if (EPI == EPI_LNRES) {  // the 8 lanes that share a row combine; one slot per (column block, column group)
+        const int parts = (N / BN) * (TC_EPI_WARPS / 4);
+        const int slot = (n0 / BN) * (TC_EPI_WARPS / 4) + ((warp - 2) >> 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+          }
+          if ((lane & 7) == 0) ln.out_stats[(size_t)(row0 + 4 * i) * parts + slot] = make_float2(s1[i], s2[i]);
+        }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -476,270 +606,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Fused projection + residual + LayerNorm (BertSelfOutput / BertOutput):
-//     out = LN(A W^T + bias + resid) * gamma + beta        and its fp16 hi / lo planes
-// CTA pairs only.  N = NH * 192 <= 384 is the whole hidden size, so each CTA of the pair owns COMPLETE
-// rows (its 128 rows x N columns live in its TMEM as NH accumulators of 192 columns) and the row
-// statistics never leave the CTA.  Epilogue, per tile:
-//   phase A  TMEM -> smem transpose -> x' = acc * scale + bias + resid (coalesced), x' parked in a
-//            global scratch that stays in L2, per-row sum / sum-of-squares accumulated in registers;
-//            the accumulator is released as soon as its last column has been read
-//   barrier  (named, epilogue warps only) + combine the two column halves through shared memory
-//   phase B  x' re-read (L2), normalised, written as fp32 + hi / lo planes - this overlaps the next
-//            tile's MMAs.
-// It removes the standalone LayerNorm kernel's HBM round trip - but see tc_gemm_ln_supported(): as measured it
-// is latency-bound and loses to the two-kernel path, so it is opt-in.
-template <int NH, int NPASS>
-struct TcLnCfg {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int W_BYTES = NH * 96 * TC_BK * 2;     // this CTA's share of the weight tile, per plane
-  static constexpr int PLANES = NPASS == 1 ? 1 : 2;
-  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-  static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;
-  static constexpr int STAT_BYTES = 2 * TC_EPI_WARPS * 32 * 2 * 4;  // double-buffered [warp][row][sum, sumsq]
-  static constexpr int BUDGET = 227 * 1024 - EPI_BYTES - STAT_BYTES - 2048;
-  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + STAT_BYTES;
-  static constexpr uint32_t TMEM_COLS = NH == 1 ? 256 : 512;
-  static_assert(STAGES >= 2, "tile too large");
-};
-
-template <int NH, int NPASS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                  const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, float ln_eps, float* __restrict__ scratch, float* __restrict__ out,
-                  __half* __restrict__ o_hi, __half* __restrict__ o_lo, int M, int K, float out_scale,
-                  int* __restrict__ err_flag) {
-  using Cfg = TcLnCfg<NH, NPASS>;
-  constexpr int N = NH * 192;
-  pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::STAGES;
-  uint64_t* acc_full = bars + 2 * Cfg::STAGES;   // [1]
-  uint64_t* acc_empty = acc_full + 1;            // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = M / (2 * TC_BM), k_blocks = K / TC_BK;
-  const int crank = (int)cluster_rank();
-  const bool leader = crank == 0;
-  const int tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 2 * 32 * TC_EPI_WARPS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_w_hi);
-    if (NPASS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w_lo); }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
-        const int m0 = (tile * 2 + crank) * TC_BM;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          if (!mbar_wait(&empty[stage], phase ^ 1)) { atomicExch(err_flag, 201); ok = false; break; }
-          uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* w_hi = s + Cfg::PLANES * Cfg::A_BYTES;
-          uint8_t* w_lo = w_hi + Cfg::W_BYTES;
-          if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_2sm(s, &map_a_hi, &full[stage], kb * TC_BK, m0, TC_EVICT_FIRST);
-          if (NPASS > 1) tma_load_2d_2sm(s + Cfg::A_BYTES, &map_a_lo, &full[stage], kb * TC_BK, m0, TC_EVICT_FIRST);
-#pragma unroll
-          for (int h = 0; h < NH; ++h) {  // column half h: this CTA stages 96 of its 192 weight rows
-            tma_load_2d_2sm(w_hi + h * 96 * 128, &map_w_hi, &full[stage], kb * TC_BK, h * 192 + crank * 96, TC_EVICT_LAST);
-            if (NPASS > 1)
-              tma_load_2d_2sm(w_lo + h * 96 * 128, &map_w_lo, &full[stage], kb * TC_BK, h * 192 + crank * 96, TC_EVICT_LAST);
-          }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_f16(192, 2 * TC_BM);
-      int stage = 0; uint32_t phase = 0, acc_phase = 0;
-      bool ok = true;
-      for (int tile = tile0; tile < n_tiles && ok; tile += tile_step) {
-        if (!mbar_wait(acc_empty, acc_phase ^ 1)) { atomicExch(err_flag, 202); break; }
-        tc_fence_after();
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          if (!mbar_wait(&full[stage], phase)) { atomicExch(err_flag, 203); ok = false; break; }
-          tc_fence_after();
-          const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t a_hi = s, a_lo = s + Cfg::A_BYTES;
-          const uint32_t w_hi = s + Cfg::PLANES * Cfg::A_BYTES, w_lo = w_hi + Cfg::W_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            const uint32_t koff = k * TC_UMMA_K * 2;
-            const uint64_t da_hi = umma_desc_sw128(a_hi + koff), da_lo = umma_desc_sw128(a_lo + koff);
-#pragma unroll
-            for (int h = 0; h < NH; ++h) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(h * 192);
-              const uint64_t dw_hi = umma_desc_sw128(w_hi + h * 96 * 128 + koff);
-              umma_f16_2sm(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-              if (NPASS > 1) {
-                const uint64_t dw_lo = umma_desc_sw128(w_lo + h * 96 * 128 + koff);
-                umma_f16_2sm(d_tmem, da_hi, dw_lo, idesc, 1u);
-                umma_f16_2sm(d_tmem, da_lo, dw_hi, idesc, 1u);
-              }
-            }
-          }
-          umma_commit_2sm_mc(&empty[stage], 3);
-          if (kb == k_blocks - 1) umma_commit_2sm_mc(acc_full, 3);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-        acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..9): bias + residual + LayerNorm + hi/lo split =====================
-    const int quad = warp & 3, chalf = (warp - 2) >> 2;
-    constexpr int COLS_PER_WARP = N / 2;             // 192 (NH = 2) or 96 (NH = 1)
-    constexpr int NCH = COLS_PER_WARP / 32;
-    constexpr int EP = Cfg::EPI_PITCH;
-    const int col_lo = chalf * COLS_PER_WARP;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 32 * EP;
-    float* stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::EPI_BYTES);
-    const int lr = lane >> 3, lc = (lane & 7) * 4;
-    uint32_t acc_phase = 0;
-    int tcount = 0;
-    for (int tile = tile0; tile < n_tiles; tile += tile_step, ++tcount) {
-      const int m0 = (tile * 2 + crank) * TC_BM;
-      if (!mbar_wait(acc_full, acc_phase)) { if (lane == 0) atomicExch(err_flag, 204); break; }
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-      float s1[8], s2[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
-      uint32_t v[32];
-      tmem_ld32_issue(t_row + (uint32_t)col_lo, v);
-      // ---- phase A ----
-#pragma unroll 1
-      for (int ci = 0; ci < NCH; ++ci) {
-        const int c0 = col_lo + ci * 32;
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * EP + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        if (ci + 1 < NCH) {
-          tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), v);
-        } else {
-          tc_fence_before();  // every TMEM read of this accumulator has completed
-          if (leader) mbar_arrive(acc_empty); else mbar_arrive_remote(acc_empty, 0);
-        }
-        const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + lc);
-        float4 rs[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          rs[i] = __ldcs(reinterpret_cast<const float4*>(resid + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + lr;
-          const float4 a = *reinterpret_cast<const float4*>(stg + r * EP + lc);
-          const float o0 = fmaf(a.x, out_scale, b4.x) + rs[i].x, o1 = fmaf(a.y, out_scale, b4.y) + rs[i].y;
-          const float o2 = fmaf(a.z, out_scale, b4.z) + rs[i].z, o3 = fmaf(a.w, out_scale, b4.w) + rs[i].w;
-          s1[i] += (o0 + o1) + (o2 + o3);
-          s2[i] = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, s2[i]))));
-          *reinterpret_cast<float4*>(scratch + (size_t)(m0 + quad * 32 + r) * N + c0 + lc) = make_float4(o0, o1, o2, o3);
-        }
-        __syncwarp();
-      }
-      // ---- row statistics: 8 lanes share a row inside the warp, two warps share it inside the CTA ----
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-        }
-      }
-      float* st = stats + (tcount & 1) * (TC_EPI_WARPS * 32 * 2);
-      if ((lane & 7) == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float2*>(st + ((warp - 2) * 32 + 4 * i + lr) * 2) = make_float2(s1[i], s2[i]);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-      float mean[8], rstd[8];
-      {
-        const int w0 = quad == 2 ? 0 : (quad == 3 ? 1 : (quad == 0 ? 2 : 3));  // epilogue-warp index of (quad, chalf 0)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + lr;
-          const float2 p0 = *reinterpret_cast<const float2*>(st + (w0 * 32 + r) * 2);
-          const float2 p1 = *reinterpret_cast<const float2*>(st + ((w0 + 4) * 32 + r) * 2);
-          const float m = (p0.x + p1.x) * (1.0f / N);
-          const float var = fmaxf((p0.y + p1.y) * (1.0f / N) - m * m, 0.0f);
-          mean[i] = m;
-          rstd[i] = 1.0f / sqrtf(var + ln_eps);
-        }
-      }
-      // ---- phase B (overlaps the next tile's MMAs) ----
-#pragma unroll 1
-      for (int ci = 0; ci < NCH; ++ci) {
-        const int c0 = col_lo + ci * 32;
-        const float4 g4 = *reinterpret_cast<const float4*>(gamma + c0 + lc);
-        const float4 e4 = *reinterpret_cast<const float4*>(beta + c0 + lc);
-        float4 xs[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          xs[i] = *reinterpret_cast<const float4*>(scratch + (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const size_t off = (size_t)(m0 + quad * 32 + 4 * i + lr) * N + c0 + lc;
-          const float o0 = ((xs[i].x - mean[i]) * rstd[i]) * g4.x + e4.x, o1 = ((xs[i].y - mean[i]) * rstd[i]) * g4.y + e4.y;
-          const float o2 = ((xs[i].z - mean[i]) * rstd[i]) * g4.z + e4.z, o3 = ((xs[i].w - mean[i]) * rstd[i]) * g4.w + e4.w;
-          __stcs(reinterpret_cast<float4*>(out + off), make_float4(o0, o1, o2, o3));
-          const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
-          uint2 ph;
-          ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-          *reinterpret_cast<uint2*>(o_hi + off) = ph;
-          if (NPASS > 1) {
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(o0 - f01.x, o1 - f01.y), l23 = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
-            uint2 pl;
-            pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
-            *reinterpret_cast<uint2*>(o_lo + off) = pl;
-          }
-        }
-      }
-      acc_phase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // operand preparation
@@ -767,10 +633,11 @@ __global__ void tc_split_kernel(const float* __restrict__ src, __half* __restric
   }
 }
 
-__global__ void tc_absmax_kernel(const float* __restrict__ src, size_t n, unsigned int* out_bits) {
+__global__ void tc_absmax_kernel(const float* __restrict__ src, size_t n, unsigned int* out_bits,
+                                 const float* __restrict__ col_gamma, int k) {
   float m = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(src[i]));
+    m = fmaxf(m, fabsf(col_gamma ? src[i] * col_gamma[i % k] : src[i]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
 }
@@ -783,27 +650,48 @@ __global__ void tc_absmax_kernel(const float* __restrict__ src, size_t n, unsign
 // weight) additionally carry the same correction for the two 16-wide chunks of the attention kernel's K = 32
 // products Q K^T and Q E^T (head dim d: chunk d / 16 of 2).  Create-time only: plain fp64 arithmetic.
 __global__ void tc_split_weight_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
-                                       int n, int k, double scale, double alpha, double beta, double beta_att, int q_rows) {
+                                       int n, int k, double scale, double alpha, double beta, double beta_att, int q_rows,
+                                       const float* __restrict__ col_gamma) {
   const size_t total = (size_t)n * k;
   const int nk = k / 16;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / k), col = (int)(i % k);
     double c = 1.0 + alpha + beta * (double)(nk - col / 16);
     if (row < q_rows) c *= 1.0 + alpha + beta_att * (double)(2 - (row % FD_HEAD_DIM) / 16);
+    if (col_gamma) c *= (double)col_gamma[col];  // LayerNorm folded into the projection: W' = W diag(gamma) (TcLn)
     const double x = (double)src[i] * scale * c;
     const __half h = __double2half(x);
     hi[i] = h;
     lo[i] = __double2half(x - (double)__half2float(h));
   }
 }
-// bias of the query rows, scaled like those rows
-__global__ void tc_scale_qbias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int q_rows,
-                                      double alpha, double beta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double c = 1.0;
-  if (i < q_rows) c = 1.0 + alpha + beta * (double)(2 - (i % FD_HEAD_DIM) / 16);
-  dst[i] = (float)((double)src[i] * c);
+// Epilogue vectors of a projection whose input LayerNorm is folded in (TcLn):
+//   c[n] = s_n * sum_k gamma[k] W[n, k],   d[n] = s_n * (sum_k beta[k] W[n, k] + b[n])
+// (gamma == nullptr: no fold - c = 0, d = s_n * b).  s_n is the attention de-bias factor of the query rows (n < q_rows).
+// One warp per output row, fp64 accumulation; create time only.
+__global__ void tc_fold_vectors_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta_ln, int n, int k, int q_rows, double alpha, double beta_att,
+                                       float* __restrict__ c_out, float* __restrict__ d_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double sc = 0.0, sd = 0.0;
+  if (gamma) {
+    for (int j = lane; j < k; j += 32) {
+      const double wv = (double)w[(size_t)row * k + j];
+      sc += (double)gamma[j] * wv;
+      sd += (double)beta_ln[j] * wv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+  }
+  if (lane == 0) {
+    const double s = row < q_rows ? 1.0 + alpha + beta_att * (double)(2 - (row % FD_HEAD_DIM) / 16) : 1.0;
+    c_out[row] = (float)(s * sc);
+    d_out[row] = (float)(s * (sd + (double)b[row]));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -878,12 +766,12 @@ inline void tc_free_acts(TcActs* a) {
 // truncation of the sum); with zero-mean products - the network's case - only the part that is a linear functional
 // of the partial sums survives on average, ~1e-7 per chunk, and that is what a static pre-scale can cancel.
 // tools/rz_sweep.py then picked beta on the real network: forward error against the fp64 oracle (production shape)
-// rms 1.03e-6 at beta = 0 -> 2.38e-7 at beta = 0.975e-7, the fp32 CUDA-core path's own 2.37e-7.
+// rms 1.03e-6 at beta = 0 -> 2.41e-7 for beta in [0.95e-7, 1.05e-7], the fp32 CUDA-core path's own 2.37e-7.
 // FOLDINGDIFF_B200_RZ="alpha,beta[,beta_attention]" overrides ("0,0" = off).
 struct TcRz { double alpha, beta, beta_att; };
 inline TcRz tc_rz() {
   static TcRz rz = [] {
-    TcRz r{0.0, 0.975e-7, 0.975e-7};
+    TcRz r{0.0, 1.0e-7, 1.0e-7};
     const char* e = getenv("FOLDINGDIFF_B200_RZ");
     if (e && e[0]) {
       char* end = nullptr;
@@ -901,13 +789,14 @@ inline TcRz tc_rz() {
 
 // fp32 [n, k] device weight -> scaled fp16 hi / lo planes + TMA maps.  Synchronous (create time).
 // q_rows: leading rows that are attention queries (fused QKV weight), see tc_split_weight_kernel.
-inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out, int q_rows = 0) {
+// col_gamma: LayerNorm weight folded into the K columns (TcLn), or nullptr.
+inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out, int q_rows = 0, const float* col_gamma = nullptr) {
   out->n = n; out->k = k; out->bn = tc_pick_bn(n);
   const size_t cnt = (size_t)n * k;
   unsigned int* bits = nullptr;
   if (cudaMalloc(&bits, sizeof(unsigned int)) != cudaSuccess) return 1;
   cudaMemset(bits, 0, sizeof(unsigned int));
-  tc_absmax_kernel<<<64, 256>>>(w_dev, cnt, bits);
+  tc_absmax_kernel<<<64, 256>>>(w_dev, cnt, bits, col_gamma, k);
   unsigned int hb = 0;
   if (cudaMemcpy(&hb, bits, sizeof(hb), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(bits); return 1; }
   cudaFree(bits);
@@ -925,7 +814,7 @@ inline int tc_pack_weight(const float* w_dev, int n, int k, TcWeight* out, int q
   if (cudaMalloc(&out->hi, sizeof(__half) * cnt) != cudaSuccess) return 1;
   if (cudaMalloc(&out->lo, sizeof(__half) * cnt) != cudaSuccess) return 1;
   const TcRz rz = tc_rz();
-  tc_split_weight_kernel<<<256, 256>>>(w_dev, out->hi, out->lo, n, k, ldexp(1.0, shift), rz.alpha, rz.beta, rz.beta_att, q_rows);
+  tc_split_weight_kernel<<<256, 256>>>(w_dev, out->hi, out->lo, n, k, ldexp(1.0, shift), rz.alpha, rz.beta, rz.beta_att, q_rows, col_gamma);
   if (cudaDeviceSynchronize() != cudaSuccess) return 1;
   if (tc_make_map(&out->map_hi, out->hi, n, k, out->bn)) return 2;
   if (tc_make_map(&out->map_lo, out->lo, n, k, out->bn)) return 2;
@@ -995,7 +884,7 @@ inline int tc_mode() {
 
 template <int BN, int NPASS, int EPI, int CL, bool PAIR>
 int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
-                 TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+                 TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st, const TcLn& ln) {
   using Cfg = TcCfg<BN, NPASS, PAIR>;
   static unsigned long long configured = 0;
   auto kern = tc_gemm_kernel<BN, NPASS, EPI, CL, PAIR>;
@@ -1026,105 +915,51 @@ int tc_launch_cl(const TcPlane* a, const TcWeight* w, const float* bias, const f
   // column tiles re-read it (measured: hurts the 6-tile QKV projection, helps the 2-tile ones)
   const unsigned long long a_policy = (N / BN <= 2) ? TC_EVICT_FIRST : 0x1000000000000000ull;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, wh, wl, bias, resid, C, c_hi, c_lo, M, N, K,
-                                     w->inv_scale, err, a_policy);
+                                     w->inv_scale, err, a_policy, ln);
   return e == cudaSuccess ? 0 : 12;
 }
 
 template <int BN, int NPASS, int EPI>
 int tc_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, float* C,
-              TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+              TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st, const TcLn& ln) {
   if (M % (2 * TC_BM) == 0 && tc_mode() == 2)
-    return tc_launch_cl<BN, NPASS, EPI, 2, true>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    return tc_launch_cl<BN, NPASS, EPI, 2, true>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
   if (M % (2 * TC_BM) == 0 && tc_mode() == 1)
-    return tc_launch_cl<BN, NPASS, EPI, 2, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
-  return tc_launch_cl<BN, NPASS, EPI, 1, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    return tc_launch_cl<BN, NPASS, EPI, 2, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
+  return tc_launch_cl<BN, NPASS, EPI, 1, false>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
 }
 
 template <int BN, int NPASS>
 int tc_dispatch_epi(int epi, const TcPlane* a, const TcWeight* w, const float* bias, const float* resid,
-                    float* C, TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st) {
+                    float* C, TcPlane* c_tc, int M, int N, int K, int sm_count, cudaStream_t st, const TcLn& ln) {
   switch (epi) {
-    case EPI_BIAS: return tc_launch<BN, NPASS, EPI_BIAS>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
-    case EPI_BIAS_GELU: return tc_launch<BN, NPASS, EPI_BIAS_GELU>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
-    default: return tc_launch<BN, NPASS, EPI_BIAS_RESID>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+    case EPI_BIAS: return tc_launch<BN, NPASS, EPI_BIAS>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
+    case EPI_BIAS_GELU: return tc_launch<BN, NPASS, EPI_BIAS_GELU>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
+    case EPI_LNIN: return tc_launch<BN, NPASS, EPI_LNIN>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
+    case EPI_LNIN_GELU: return tc_launch<BN, NPASS, EPI_LNIN_GELU>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
+    case EPI_LNRES: return tc_launch<BN, NPASS, EPI_LNRES>(a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
   }
+  return 22;  // EPI_BIAS_RESID belongs to the fp32 CUDA-core GEMM only
 }
 
 // mode: 1 = FD_GEMM_TC_3X, 2 = FD_GEMM_TC_1X
 inline int tc_gemm(int mode, int epi, const TcPlane* a, const TcWeight* w, const float* bias,
                    const float* resid, float* C, TcPlane* c_tc, int M, int N, int K, int sm_count,
-                   cudaStream_t st) {
+                   cudaStream_t st, const TcLn& ln = TcLn()) {
   if (!a || !w || M % TC_BM || K % TC_BK || N % w->bn || a->k != K || w->k != K || w->n != N) return 20;
   const bool three = mode == 1;
   switch (w->bn) {
     case 192:
-      return three ? tc_dispatch_epi<192, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
-                   : tc_dispatch_epi<192, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+      return three ? tc_dispatch_epi<192, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln)
+                   : tc_dispatch_epi<192, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
     case 128:
-      return three ? tc_dispatch_epi<128, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
-                   : tc_dispatch_epi<128, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+      return three ? tc_dispatch_epi<128, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln)
+                   : tc_dispatch_epi<128, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
     case 64:
-      return three ? tc_dispatch_epi<64, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st)
-                   : tc_dispatch_epi<64, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st);
+      return three ? tc_dispatch_epi<64, 3>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln)
+                   : tc_dispatch_epi<64, 1>(epi, a, w, bias, resid, C, c_tc, M, N, K, sm_count, st, ln);
   }
   return 21;
-}
-
-
-// out = LN(a W^T + bias + resid) * gamma + beta as fp32 + hi/lo planes; N = w->n in {192, 384}; needs M % 256 == 0.
-// mode: 1 = FD_GEMM_TC_3X, 2 = FD_GEMM_TC_1X.  Returns 0 on success.
-template <int NH, int NPASS>
-int tc_gemm_ln_launch(const TcPlane* a, const TcWeight* w, const float* bias, const float* resid, const float* gamma,
-                      const float* beta, float eps, float* scratch, float* out, TcPlane* o_tc, int M, int K,
-                      int sm_count, cudaStream_t st) {
-  using Cfg = TcLnCfg<NH, NPASS>;
-  static unsigned long long configured = 0;
-  auto kern = tc_gemm_ln_kernel<NH, NPASS>;
-  if (tc_need_configure(&configured) &&
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return 10;
-  int* err = tc_err_flag();
-  if (!err) return 11;
-  const int tiles = M / (2 * TC_BM);
-  int clusters = sm_count / 2;
-  if (tiles < clusters) clusters = tiles;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * 2));
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a->map_hi, a->map_lo, w->half_hi, w->half_lo, bias, resid, gamma, beta,
-                                     eps, scratch, out, o_tc->hi, NPASS > 1 ? o_tc->lo : (__half*)nullptr, M, K,
-                                     w->inv_scale, err);
-  return e == cudaSuccess ? 0 : 12;
-}
-
-inline bool tc_gemm_ln_supported(const TcWeight* w, int M) {
-  // Opt-in (FOLDINGDIFF_B200_FUSE_LN=1).  Measured on B200, config 2: the fused kernel is numerically
-  // equivalent but SLOWER than GEMM + standalone LayerNorm (2.67 vs 2.31 ms per reverse step for the two
-  // projections): ~1 MB of residual / scratch / output traffic per tile is latency-exposed behind only 8
-  // epilogue warps per SM, and 175 full-row tiles over 74 CTA pairs quantise to 3 waves, while the
-  // standalone LayerNorm streams at the HBM roofline with thousands of warps in flight.
-  static const bool enabled = [] { const char* e = getenv("FOLDINGDIFF_B200_FUSE_LN"); return e && e[0] == '1'; }();
-  return enabled && tc_mode() == 2 && w->bn == 192 && (w->n == 192 || w->n == 384) && M % (2 * TC_BM) == 0;
-}
-
-inline int tc_gemm_ln(int mode, const TcPlane* a, const TcWeight* w, const float* bias, const float* resid,
-                      const float* gamma, const float* beta, float eps, float* scratch, float* out, TcPlane* o_tc,
-                      int M, int K, int sm_count, cudaStream_t st) {
-  if (!a || !w || !o_tc || a->k != K || w->k != K || K % TC_BK) return 20;
-  const bool three = mode == 1;
-  if (w->n == 384)
-    return three ? tc_gemm_ln_launch<2, 3>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st)
-                 : tc_gemm_ln_launch<2, 1>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st);
-  return three ? tc_gemm_ln_launch<1, 3>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st)
-               : tc_gemm_ln_launch<1, 1>(a, w, bias, resid, gamma, beta, eps, scratch, out, o_tc, M, K, sm_count, st);
 }
 
 }  // namespace fd

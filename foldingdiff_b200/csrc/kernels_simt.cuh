@@ -130,7 +130,8 @@ layernorm_kernel(const float* __restrict__ in, const float* __restrict__ resid, 
 // 128 x 64 x 16 tiles, 256 threads, 8 x 4 register micro-tile, register-prefetch double buffer.
 // M % 128 == 0, N % 64 == 0, K % 16 == 0 (the caller pads the row count).
 // ------------------------------------------------------------------------------------------------
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2,
+       EPI_LNIN = 3, EPI_LNIN_GELU = 4, EPI_LNRES = 5 };  // tensor-core path only: LayerNorm folded into the projections (gemm_tc.cuh: TcLn)
 
 template <int EPI>
 __global__ void __launch_bounds__(256)

@@ -5,7 +5,7 @@ from foldingdiff_b200 import modelling, synthetic
 
 GEMMS = ["fp32", "tc3x"]
 # max-abs tolerance on eps_hat against the fp32 CPU oracle, per GEMM arithmetic
-FWD_TOL = {"fp32": 1e-5, "tc3x": 2e-5}
+FWD_TOL = {"fp32": 1e-5, "tc3x": 1e-5}  # measured (B200): 1.1e-6 fp32, 1.5e-6 tc3x at production shape
 
 
 def mini_model(mini_dir, gemm):

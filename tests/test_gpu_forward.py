@@ -112,7 +112,7 @@ def test_to_device_roundtrip_and_state_dict(mini_dir):
 
 
 @pytest.mark.parametrize("env", [{"FOLDINGDIFF_B200_TC_MODE": "mcast"}, {"FOLDINGDIFF_B200_TC_MODE": "single"},
-                                 {"FOLDINGDIFF_B200_FUSE_LN": "1"}, {"FOLDINGDIFF_B200_ATT": "pool"}])
+                                 {"FOLDINGDIFF_B200_ATT": "pool"}])
 def test_alternative_tensor_core_paths(env, tmp_path):
     """The A/B variants of the tensor-core path (multicast clusters, single CTA, fused GEMM+LayerNorm, the other
     attention kernels) are

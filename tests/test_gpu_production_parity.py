@@ -117,7 +117,7 @@ def test_config2_teacher_forced_steps_against_cpu_oracle(prod_oracle, gemm):
             x = ref
     print(f"[{gemm}] config-2 teacher-forced, 24 steps x 8 chains: first step (x100 gain) {worst_first:.3e}, others {worst:.3e}")
     assert worst < 1e-5 if gemm == "fp32" else worst < 2e-5
-    assert worst_first < 1.5e-4
+    assert worst_first < 2e-4
 
 
 def test_config5_partial_denoise_b512(prod_oracle):

@@ -3,8 +3,8 @@ Parity of the reverse-diffusion loop (fd_p_sample_steps through sampling.*) agai
 and the golden histories written by the reference's own loop.
 
 Gate (tolerance of BASELINE.json north_star = 1e-4 max-abs fp32):
-  (2) teacher-forced single steps      <= 1e-4 for every t, except t = T-1 of the cosine schedule
-                                          where 1/sqrt(alpha) = 100 amplifies the forward error (<= 2e-3)
+  (2) teacher-forced single steps      <= 1e-5 for every t, except t = T-1 of the cosine schedule
+                                          where 1/sqrt(alpha) = 100 amplifies the forward error (<= 2e-4)
   (3) well-conditioned chains          <= 1e-4 circular max-abs (linear schedule; partial denoise)
   (4) full cosine chain from t = T     ill-conditioned for ANY fp32 implementation (a 1e-7 relative
                                           jitter of the oracle's own output gives 1.7e-3): report
@@ -76,8 +76,8 @@ def test_teacher_forced_steps(mini_dir, gemm, tag, schedule):
             else:
                 worst = max(worst, d)
     print(f"[{gemm}] {tag}: teacher-forced max err first step {worst_first:.3e}, other steps {worst:.3e}")
-    assert worst < 1e-4
-    assert worst_first < (2e-3 if schedule == "cosine" else 1e-4)
+    assert worst < 1e-5  # every step but the first: at the fp32 floor in both arithmetics
+    assert worst_first < (2e-4 if schedule == "cosine" else 1e-5)  # x100 gain at t = T-1: 1.2e-4 (fp32) / 1.3e-4 .. 1.7e-4 (tc3x)
 
 
 @pytest.mark.parametrize("gemm", GEMMS)
@@ -99,7 +99,7 @@ def test_linear_chain_matches_reference_loop_golden(mini_dir, gemm, monkeypatch)
         worst = max(worst, float(oloop.circular_abs_diff(out[:, i, :l], hist[:, i, :l], ANG).max()))
         assert float(out[:, i, l:].abs().max()) == 0.0 if l < 64 else True  # padded history rows are 0
     print(f"[{gemm}] linear T=100 chain: max circular err over the whole history {worst:.3e}")
-    assert worst < 1e-4
+    assert worst < 2e-5  # gate 1e-4; measured 5.7e-6 (fp32) / 6-8e-6 (tc3x, de-biased; 4.8e-5 .. 7.7e-5 before)
     final_only = None
     torch.manual_seed(SEED)
     torch.randn(4, 128, 6)
@@ -124,8 +124,10 @@ def test_cosine_config1_chain_statistics(mini_dir, gemm, monkeypatch):
     frac = float((d < 1e-4).float().mean())
     print(f"[{gemm}] cosine T=100 chain from t=T: final max {float(d.max()):.3e}, median {float(d.median()):.3e}, "
           f"fraction < 1e-4 = {frac:.3f}; first step max {float(oloop.circular_abs_diff(out[0], hist[0], ANG).max()):.3e}")
-    # fp32 CUDA cores: median ~4e-6, ~95% of entries < 1e-4; 3-pass tensor cores (RZ accumulate): ~7e-5, ~55%
-    assert float(d.median()) < 2e-4 and frac > (0.8 if gemm == "fp32" else 0.4)
+    # fp32 CUDA cores: median 4e-6, 95% of entries < 1e-4.  3-pass tensor cores: median 8e-5 / 54% before the accumulation
+    # de-bias (gemm_tc.cuh: tc_rz), median ~1e-5 / 85-88% with it (profiles/r02_rz_calibration.md); what is left between
+    # the two arithmetics is which way the chaotic tail of this ill-conditioned chain falls, not a systematic error
+    assert float(d.median()) < 2e-5 and frac > (0.9 if gemm == "fp32" else 0.8)
     assert float(out.abs().max()) <= np.pi  # every column is angular and wrapped into [-pi, pi)
     # distributional agreement of the final structures (SURVEY.md section 8c protocol (4)): per-feature circular mean
     # and dispersion over the 4 x 64 residues must match the reference chain even where single angles have diverged

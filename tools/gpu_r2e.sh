@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 call E: per-warpgroup TMEM regions in the attention kernel + the epilogue statistics fix.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; echo "build rc=$?"
+timeout 300 python -m pytest tests/test_gpu_attention.py -m gpu -q -s -x > gpurun_out/test_att.log 2>&1; echo "attention tests rc=$?"; tail -15 gpurun_out/test_att.log
+timeout 900 python -m pytest tests/test_gpu_forward.py tests/test_gpu_gemm.py tests/test_gpu_sampling.py tests/test_gpu_edges.py -m gpu -q -s > gpurun_out/test_gpu_core.log 2>&1; echo "core gpu tests rc=$?"
+grep -E "^\.*\[|passed|failed|rror|FAIL|assert" gpurun_out/test_gpu_core.log | sed 's/^\.*//' | grep -v "^\[build\]" | tail -30
+timeout 600 python bench.py --no-cpu-baseline --no-e2e --no-extra-workloads --steps 2 --warmup 3 > gpurun_out/bench_e.json 2> gpurun_out/bench_e.err; echo "bench rc=$?"
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_e.json"))
+    print("value", round(d["value"], 2), "ms/pass", round(d["ms_per_step"], 1), "clocks", d["clocks"], "parity", d.get("parity"))
+    print({k: round(v['ms_per_reverse_step'], 3) for k, v in d['kernels'].items()}, "sum", round(sum(v['ms_per_reverse_step'] for v in d['kernels'].values()), 3))
+except Exception as e:
+    print("bench parse failed", e); print(open("gpurun_out/bench_e.err").read()[-2500:])
+PY
+bash tools/gpu_ncu_step.sh
