@@ -23,15 +23,29 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale() -> bool:
-    if not os.path.isfile(LIB_PATH):
-        return True
-    built = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
+SHA_PATH = LIB_PATH + ".src_sha"  # hash of the sources the library was built from (travels with the .so)
+
+
+def source_sha() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
         p = os.path.join(CSRC, f)
-        if os.path.isfile(p) and os.path.getmtime(p) > built:
-            return True
-    return False
+        if os.path.isfile(p):
+            h.update(os.path.basename(p).encode())
+            with open(p, "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    """The library is stale when it was built from other sources than the ones in the tree: decided by content hash,
+    not by mtime (a checkout or a copy to the GPU box changes mtimes arbitrarily; a stale .so must never be reused)."""
+    if not os.path.isfile(LIB_PATH) or not os.path.isfile(SHA_PATH):
+        return True
+    with open(SHA_PATH) as f:
+        return f.read().strip() != source_sha()
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
@@ -42,6 +56,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if verbose:
         print("[foldingdiff_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)
+    with open(SHA_PATH, "w") as f:
+        f.write(source_sha() + "\n")
     return LIB_PATH
 
 

@@ -289,9 +289,6 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
   }
   const float inv_n = 1.0f / (float)Hd;
   const int parts = H->stat_parts;
-  // FOLDINGDIFF_B200_RESID=planes (experiment): the residual source of a LayerNorm site is read back from the fp16
-  // hi / lo planes of the raw rows (22-bit) and no fp32 copy is written: 12 instead of 16 bytes per element and site
-  static const bool res_planes = [] { const char* e = getenv("FOLDINGDIFF_B200_RESID"); return e && e[0] == 'p'; }();
   for (int l = 0; l < H->d.layers; ++l) {
     LayerW& w = H->layers[l];
     const LayerW* prev = l > 0 ? &H->layers[l - 1] : nullptr;
@@ -303,10 +300,10 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
     rc = launch_attention_mma(H, w, st);
     if (rc) return rc;
     fd::TcLn r1;  // attention-output site: residual = the layer input = embedding output (l = 0) or LN2 of layer l - 1
-    r1.res_v = res_planes ? nullptr : H->h; r1.res_hi = H->tc.h.hi; r1.res_lo = H->tc.h.lo;
+    r1.res_v = H->h;
     r1.out_stats = H->stats1; r1.inv_n = inv_n; r1.eps = H->d.ln_eps;
     if (prev) { r1.res_stats = H->stats2; r1.res_g = prev->ln2_g; r1.res_b = prev->ln2_b; r1.res_parts = parts; }
-    rc = project(H, CAT_GEMM_OUT, fd::EPI_LNRES, nullptr, nullptr, &w.to, w.b_o, nullptr, res_planes ? nullptr : H->a, Hd, Hd,
+    rc = project(H, CAT_GEMM_OUT, fd::EPI_LNRES, nullptr, nullptr, &w.to, w.b_o, nullptr, H->a, Hd, Hd,
                  &H->tc.ctx, &H->tc.a, st, r1);
     if (rc) return rc;
     fd::TcLn in1;
@@ -315,9 +312,9 @@ int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride
                  &H->tc.inter, st, in1);
     if (rc) return rc;
     fd::TcLn r2;  // FFN-output site: residual = LN1 of this layer
-    r2.res_v = res_planes ? nullptr : H->a; r2.res_hi = H->tc.a.hi; r2.res_lo = H->tc.a.lo; r2.res_stats = H->stats1; r2.res_g = w.ln1_g; r2.res_b = w.ln1_b; r2.res_parts = parts;
+    r2.res_v = H->a; r2.res_stats = H->stats1; r2.res_g = w.ln1_g; r2.res_b = w.ln1_b; r2.res_parts = parts;
     r2.out_stats = H->stats2; r2.inv_n = inv_n; r2.eps = H->d.ln_eps;
-    rc = project(H, CAT_GEMM_FFN2, fd::EPI_LNRES, nullptr, nullptr, &w.to2, w.b_o2, nullptr, res_planes ? nullptr : H->h, Hd, I,
+    rc = project(H, CAT_GEMM_FFN2, fd::EPI_LNRES, nullptr, nullptr, &w.to2, w.b_o2, nullptr, H->h, Hd, I,
                  &H->tc.inter, &H->tc.h, st, r2);
     if (rc) return rc;
   }
@@ -575,7 +572,7 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
     FD_CUDA(cudaMalloc(&h->a, sizeof(float) * r * Hd));
     FD_CUDA(cudaMalloc(&h->inter, sizeof(float) * r * I));
     if (fd::tc_alloc_acts(&h->tc, rows_pad, Hd, I)) return fail(FD_ERR_CUDA, "tensor-core workspace allocation failed");
-    h->stat_parts = 2 * Hd / fd::tc_pick_bn(Hd);
+    h->stat_parts = 2 * Hd / fd::tc_pick_bn(Hd);  // one slot per (column block, epilogue column group)
     FD_CUDA(cudaMalloc(&h->stats1, sizeof(float2) * r * h->stat_parts));
     FD_CUDA(cudaMalloc(&h->stats2, sizeof(float2) * r * h->stat_parts));
     FD_CUDA(cudaMemsetAsync(h->stats1, 0, sizeof(float2) * r * h->stat_parts, st));

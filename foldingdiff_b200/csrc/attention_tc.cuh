@@ -22,8 +22,8 @@
 // TMA, 64-byte swizzle, into a 3-slot ring.
 //
 // Warp roles (384 threads, one persistent CTA per SM):  warps 0..3 and 4..7 = two softmax warpgroups that take
-// alternate items, warp 8 = TMA producer, warp 9 = S / R MMA issuer + TMEM owner, warp 10 = P V MMA issuer (warp 11
-// only pads the producer warpgroup so that setmaxnreg can move its registers to the softmax threads).
+// alternate items, warp 8 = TMA producer, warp 9 = S / R MMA issuer + TMEM owner, warps 10 / 11 = P V MMA issuers of
+// warpgroup 0's / warpgroup 1's items.
 //
 // TMEM (512 columns), round-2 layout: every warpgroup owns a 128-column region, the relative-key product is shared -
 //     warpgroup w:  [128 w, 128 w + 128)   S [0, nk32)  ->  P round 0 (keys 0..63) hi [0, 32) lo [32, 64) | O [64, 96) |
@@ -323,14 +323,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 10) {
-    // ===================== MMA issuer 2: O = P V =====================
-    // A thread of its own: with one issuer walking S/R(it), PV(it-1), S/R(it+1), ... in program order the S / R
+  } else {
+    // ===================== MMA issuers 2 and 3 (warps 10, 11): O = P V of warpgroup 0's / warpgroup 1's items ==========
+    // Threads of their own: with one issuer walking S/R(it), PV(it-1), S/R(it+1), ... in program order the S / R
     // products of the next item queued behind the P hand-off of the previous one - on the softmax warpgroups'
-    // critical path (ncu: they spent most of their wait time on sr_full).
+    // critical path (ncu, round 1: they spent most of their wait time on sr_full).  One P V issuer PER warpgroup since
+    // round 2: a single one walks the items in order and a warpgroup whose P is ready waits behind the other
+    // warpgroup's unfinished round (ncu: 13 % of all samples in the o_full wait).
     if (lane == 0) {
       bool ok = true;
-      for (int j = 0; j < n_it && ok; ++j) {
+      for (int j = warp - 10; j < n_it && ok; j += 2) {
         {  // ---- O = P V of item j, 64 keys per round, inside the item's warpgroup region
           const int slot = j % ATC_SLOTS, w = j & 1;
           const uint32_t wpar = (uint32_t)((j >> 1) & 1);

@@ -77,8 +77,6 @@ struct TcLn {
   const float2* in_stats = nullptr;   // consumer: [rows][in_parts] partial (sum, sum of squares) of the A rows
   const float* in_c = nullptr;        //           c[n]  (d[n] travels as `bias`)
   int in_parts = 0;
-  const __half* res_hi = nullptr;     // producer: residual source rows as fp16 hi / lo planes (used when res_v is null)
-  const __half* res_lo = nullptr;
   const float* res_v = nullptr;       // producer: residual source rows (fp32) ...
   const float2* res_stats = nullptr;  //           ... normalised with these sums (nullptr: used as they are)
   const float* res_g = nullptr;
@@ -289,14 +287,9 @@ struct TcCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 };
 
-// four consecutive residual-source values: fp32 rows, or their fp16 hi + lo planes
+// four consecutive residual-source values
 __device__ __forceinline__ float4 tc_load_res4(const TcLn& ln, const float* plain, size_t off) {
-  if (plain) return *reinterpret_cast<const float4*>(plain + off);
-  if (ln.res_v) return *reinterpret_cast<const float4*>(ln.res_v + off);
-  const uint2 a = *reinterpret_cast<const uint2*>(ln.res_hi + off), b = *reinterpret_cast<const uint2*>(ln.res_lo + off);
-  const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a23 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-  const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b23 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
-  return make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+  return *reinterpret_cast<const float4*>((plain ? plain : ln.res_v) + off);
 }
 
 template <int BN, int NPASS, int EPI, int CL, bool PAIR>
@@ -495,13 +488,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
       }
+      // Two cheap pieces of software pipelining (measured on one box, profiles/r02_experiments.md: -1.1 % per pass):
+      //   COLPREF   the 16-byte bias / c vectors of chunk k + 1 are loaded while chunk k is processed (LNIN variants only:
+      //             the LNRES variant sits at the 168-register cap - 10 warps put 3 on one SM sub-partition - and spills)
+      //   RESEARLY  the first chunk's residual rows go out before the accumulator is waited for (independent of it)
+      // A full cross-tile pipeline of every epilogue load (residual rows, statistics, vectors) was built and measured
+      // SLOWER for the LNIN variants (+7 %) and only 1 - 3 % faster for LNRES; it is not kept.
+      constexpr bool COLPREF = LNIN;
+      constexpr bool RESEARLY = true;
+      float4 nb4 = make_float4(0.f, 0.f, 0.f, 0.f), nc4 = nb4;
+      if (COLPREF) {
+        nb4 = *reinterpret_cast<const float4*>(bias + n0 + col_lo + lc);
+        nc4 = *reinterpret_cast<const float4*>(ln.in_c + n0 + col_lo + lc);
+      }
+      float4 rs[8];  // residual rows of the chunk being processed (issued one chunk ahead)
+      if (RESEARLY && (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES)) {  // independent of the accumulator: before the wait
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rs[i] = tc_load_res4(ln, EPI == EPI_LNRES ? nullptr : resid, (size_t)(row0 + 4 * i) * N + n0 + col_lo + lc);
+      }
       if (!mbar_wait(&acc_full[acc], acc_phase)) { if (lane == 0) atomicExch(err_flag, 104); break; }
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       uint32_t v[32];
       tmem_ld32_issue(t_row + (uint32_t)col_lo, v);
-      float4 rs[8];  // residual rows of the chunk being processed (issued one chunk ahead)
-      if (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES) {
+      if (!RESEARLY && (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES)) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           rs[i] = tc_load_res4(ln, EPI == EPI_LNRES ? nullptr : resid, (size_t)(row0 + 4 * i) * N + n0 + col_lo + lc);
@@ -521,12 +532,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (PAIR && !leader) mbar_arrive_remote(&acc_empty[acc], 0);  // the leader's MMA warp owns the barrier
           else mbar_arrive(&acc_empty[acc]);
         }
-        const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + lc);
-        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = c4, e4 = c4;
-        if (LNIN) c4 = *reinterpret_cast<const float4*>(ln.in_c + n0 + c0 + lc);
-        if (EPI == EPI_LNRES && ln.res_stats) {
-          g4 = *reinterpret_cast<const float4*>(ln.res_g + n0 + c0 + lc);
-          e4 = *reinterpret_cast<const float4*>(ln.res_b + n0 + c0 + lc);
+        float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = c4, e4 = c4;
+        if (COLPREF) {  // this chunk's vectors were loaded one chunk ago; the next chunk's go out now
+          b4 = nb4; c4 = nc4;
+          if (ci + 1 < NCH) {
+            nb4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + 32 + lc);
+            nc4 = *reinterpret_cast<const float4*>(ln.in_c + n0 + c0 + 32 + lc);
+          }
+        } else {
+          b4 = *reinterpret_cast<const float4*>(bias + n0 + c0 + lc);
+          if (LNIN) c4 = *reinterpret_cast<const float4*>(ln.in_c + n0 + c0 + lc);
+          if (EPI == EPI_LNRES && ln.res_stats) {
+            g4 = *reinterpret_cast<const float4*>(ln.res_g + n0 + c0 + lc);
+            e4 = *reinterpret_cast<const float4*>(ln.res_b + n0 + c0 + lc);
+          }
         }
         float4 rcur[8];
         if (EPI == EPI_BIAS_RESID || EPI == EPI_LNRES) {

@@ -51,3 +51,21 @@ def test_create_fails_loudly_without_gpu():
     assert rc == 2  # FD_ERR_CUDA
     assert b"no CPU fallback" in lib.fd_last_error() or b"CUDA" in lib.fd_last_error()
     assert lib.fd_set_batch(None, 1, 1, None, 0, None, None) == 1  # FD_ERR_INVALID on null handle
+
+
+def test_library_staleness_is_decided_by_source_hash(tmp_path):
+    """build() reuses the in-tree .so only when it was built from exactly the sources in the tree (content hash recorded
+    next to it), whatever the mtimes say - a stale library must never be what the GPU tests load."""
+    assert os.path.isfile(_build.SHA_PATH), "built by an older _build: run python -m foldingdiff_b200._build"
+    assert not _build._stale()
+    recorded = open(_build.SHA_PATH).read()
+    try:
+        os.utime(os.path.join(_build.CSRC, "api.cu"))          # newer mtime, same content: still fresh
+        assert not _build._stale()
+        with open(_build.SHA_PATH, "w") as f:                    # a library built from other sources: stale
+            f.write("0" * 64 + "\n")
+        assert _build._stale()
+    finally:
+        with open(_build.SHA_PATH, "w") as f:
+            f.write(recorded)
+    assert not _build._stale()
