@@ -500,7 +500,11 @@ def main():
                     "whole_step_tflops_algorithmic": flops_step * start_t / (ms_per_step * 1e-3) / 1e12,
                     "note": "algorithmic FLOPs (valid tokens, 2 flop/MAC, SURVEY 8d) / CUDA-event kernel time; "
                             "the 3-pass split issues 3x these MMAs; ncu figures come from the committed capture named in "
-                            "ncu_profile (stale = the CUDA sources have changed since it was taken)"}
+                            "ncu_profile (stale = the CUDA sources have changed since it was taken). Since round 2 the "
+                            "projection launches ALSO do the two LayerNorms of every layer and their residual traffic (folded "
+                            "into the epilogues, 24 LayerNorm launches per reverse step removed): on that basis round 1 was "
+                            "GEMM 3.65 ms + LayerNorm 1.10 ms = 4.75 ms per reverse step = 268 TFLOP/s algorithmic = 0.186 of the "
+                            "same peak (BENCH_r01: 0.242 for the GEMM launches alone)"}
 
     # ---- section 8f rank-1 row: batched NeRF (angles -> backbone coordinates), reported beside the headline ----
     nerf_line = None

@@ -68,6 +68,7 @@ SIGNATURES = {
     "fd_debug_attention": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fd_debug_tc_status": (C.c_int32, []),
+    "fd_debug_graph_state": (C.c_int32, [C.c_void_p]),
     "fd_debug_attention_dump": (C.c_int32, [C.c_void_p]),
     "fd_write_angles_csv_gz": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), C.c_char_p,
                                            C.c_int32]),

@@ -93,6 +93,19 @@ struct fd_handle {
   // Device-side pipeline error flag (gemm_tc.cuh: bounded mbarrier waits), mirrored into pinned host memory by an
   // async copy at the end of every forward / step window and checked at the next entry point and by fd_status().
   int* host_flag = nullptr;
+  // One reverse step as a CUDA graph (run_steps): captured once per (batch, arithmetic, x buffer, wrap mask), replayed
+  // for every further step with the step's own arguments in `dyn_dev` (kernels_simt.cuh: StepDyn).
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  fd::StepDyn* dyn_dev = nullptr;
+  long long batch_gen = 0, graph_gen = -1;
+  int graph_mode = -1;
+  const float* graph_x = nullptr;
+  uint32_t graph_wrap = 0;
+  long long graph_launches = 0;  // kernels per replay
+  bool graph_broken = false;     // a capture failed once: stay on the eager path
   // optional CUDA-event profiler (fd_profile_begin / fd_profile_end)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs: start, stop
@@ -152,13 +165,13 @@ void free_batch(fd_handle* h) {
 
 template <int VPL>
 void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stride, fd::TcPlane* planes,
-                  cudaStream_t st) {
+                  cudaStream_t st, const fd::StepDyn* dyn = nullptr) {
   const int blocks = (H->rows * 32 + 255) / 256;
   ProfScope ps(H, CAT_EMBED, st);
   fd::launch_pdl(fd::embed_kernel<VPL>, dim3(blocks), dim3(256), 0, st, x, H->row_src, H->rows, H->n_pad, H->d.n_features,
                  H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps, temb, temb_stride, H->h,
                  planes ? planes->hi : (__half*)nullptr,
-                 (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : (__half*)nullptr);
+                 (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : (__half*)nullptr, dyn);
   H->launches++;
 }
 
@@ -227,13 +240,13 @@ int launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
 
 template <int VPL, bool SAMPLE>
 void launch_tail(fd_handle* H, float* eps_out, float* x, fd::StepNoise noise, float* hist,
-                 fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st) {
+                 fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st, const fd::StepDyn* dyn = nullptr) {
   const int blocks = (H->rows * 32 + 255) / 256;
   const size_t smem = sizeof(float) * H->d.n_features * H->d.hidden;
   ProfScope ps(H, CAT_TAIL, st);
   fd::launch_pdl(fd::tail_kernel<VPL, SAMPLE>, dim3(blocks), dim3(256), smem, st, (const float*)H->tmp,
                  (const int*)H->row_src, H->rows, H->d.n_features, (const float*)H->hln_g, (const float*)H->hln_b,
-                 H->d.head_ln_eps, (const float*)H->w_d2, (const float*)H->b_d2, eps_out, x, noise, hist, coef, wrap_bits);
+                 H->d.head_ln_eps, (const float*)H->w_d2, (const float*)H->b_d2, eps_out, x, noise, hist, coef, wrap_bits, dyn);
   H->launches++;
 }
 
@@ -266,10 +279,11 @@ int project(fd_handle* H, int cat, int epi, const float* A, const float* W, cons
 //   buffers: h / tc.h = the embedding output (layer 0) or v of the FFN-output site; a / tc.a = v of the attention-output
 //   site; stats2 / stats1 = their row sums.
 template <int VPL>
-int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st) {
+int run_encoder(fd_handle* H, const float* x, const float* temb, int temb_stride, cudaStream_t st,
+                const fd::StepDyn* dyn = nullptr) {
   const int Hd = H->d.hidden, I = H->d.intermediate;
   const bool tcm = H->gemm_mode != FD_GEMM_FP32_SIMT;
-  launch_embed<VPL>(H, x, temb, temb_stride, tcm ? &H->tc.h : nullptr, st);
+  launch_embed<VPL>(H, x, temb, temb_stride, tcm ? &H->tc.h : nullptr, st, dyn);
   if (!tcm) {
     for (int l = 0; l < H->d.layers; ++l) {
       LayerW& w = H->layers[l];
@@ -401,6 +415,18 @@ int32_t fd_create(const fd_dims* dims, const float* const* weights, int32_t n_we
     return fail(FD_ERR_CUDA, "pinned status word: %s", cudaGetErrorString(cudaGetLastError()));
   }
   *h->host_flag = 0;
+  if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc((void**)&h->dyn_dev, sizeof(fd::StepDyn)) != cudaSuccess) {
+    const int rc0 = fail(FD_ERR_CUDA, "step-graph resources: %s", cudaGetErrorString(cudaGetLastError()));
+    if (h->gstream) cudaStreamDestroy(h->gstream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
+    cudaFreeHost(h->host_flag);
+    delete h;
+    return rc0;
+  }
   if (!fd::tc_err_flag()) { cudaFreeHost(h->host_flag); delete h; return fail(FD_ERR_CUDA, "pipeline error flag allocation failed"); }
   h->d = d;
   h->device = device;
@@ -492,6 +518,12 @@ void fd_destroy(fd_handle* h) {
   DevGuard guard(h->device);
   cudaDeviceSynchronize();  // the pinned status word may still be the target of an enqueued copy
   if (h->host_flag) cudaFreeHost(h->host_flag);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  cudaFree(h->dyn_dev);
   free_batch(h);
   for (auto& w : h->layers) { fd::tc_free_weight(&w.tq); fd::tc_free_weight(&w.to); fd::tc_free_weight(&w.ti); fd::tc_free_weight(&w.to2); }
   fd::tc_free_weight(&h->td1);
@@ -597,6 +629,7 @@ int32_t fd_set_batch(fd_handle* h, int32_t batch, int32_t n_pad, const int32_t* 
   }
   // pageable-memory async copies have been staged by the time the call returns
   h->batch = batch; h->n_pad = n_pad; h->rows = (int)rows; h->rows_pad = rows_pad; h->all_rows = all_rows;
+  h->batch_gen++;  // any captured step graph refers to the previous batch's geometry / buffers
   return FD_OK;
 }
 
@@ -628,10 +661,49 @@ int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, floa
   return flag_enqueue_copy(h, st);
 }
 
+}  // extern "C"
+
 namespace {
+
+// FOLDINGDIFF_B200_GRAPH=0 replays nothing: every step is launched kernel by kernel on the caller's stream.
+bool graphs_enabled() {
+  static const bool on = [] { const char* e = getenv("FOLDINGDIFF_B200_GRAPH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <int V>
+int capture_step_graph(fd_handle* h, float* x_dev, uint32_t wrap_bits) {
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  const long long before = h->launches;
+  FD_CUDA(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeThreadLocal));
+  fd::StepCoef none{};
+  fd::StepNoise no_noise{nullptr, 0ull, 0ull};
+  int rc = run_encoder<V>(h, x_dev, h->time_table, 0, h->gstream, h->dyn_dev);
+  if (!rc) launch_tail<V, true>(h, nullptr, x_dev, no_noise, nullptr, none, wrap_bits, h->gstream, h->dyn_dev);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->gstream, &g);
+  h->graph_launches = h->launches - before;
+  h->launches = before;  // nothing ran: replays are counted when they are launched
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess || !g) return fail(FD_ERR_CUDA, "step graph capture failed: %s", cudaGetErrorString(e));
+  h->graph = g;
+  if (cudaGraphInstantiate(&h->gexec, h->graph, 0) != cudaSuccess) {
+    h->gexec = nullptr;
+    return fail(FD_ERR_CUDA, "step graph instantiation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return FD_OK;
+}
 
 // Reverse steps t = t_hi-1 .. t_lo; the k-th executed step takes its normals from noise_dev slice k, or (noise_dev
 // == nullptr, philox) from elements [offset + k * slice, +slice) of the library stream `seed`.
+//
+// Execution: the first step of a new (batch, arithmetic, x buffer, wrap mask) combination is launched kernel by kernel
+// on the caller's stream (it also performs every lazy one-time initialisation); the 63-launch sequence is then captured
+// ONCE into a CUDA graph on the handle's own stream and every further step is one cudaGraphLaunch preceded by a
+// 56-byte stream-ordered upload of the step's arguments (StepDyn).  The handle's stream is ordered after the caller's
+// stream on entry and the caller's stream after it on exit (events), so the call keeps its contract: work is enqueued
+// behind whatever the caller enqueued before, and whatever the caller enqueues next runs after the steps.
 int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise_dev, bool philox, uint64_t seed,
               uint64_t offset, float* history_dev, const uint8_t* wrap_mask, cudaStream_t st) {
   if (h->batch == 0) return fail(FD_ERR_STATE, "fd_set_batch has not been called");
@@ -645,6 +717,8 @@ int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise
   uint32_t wrap_bits = 0;
   for (int f = 0; f < F; ++f) wrap_bits |= (wrap_mask[f] ? 1u : 0u) << f;
   const size_t slice = (size_t)h->batch * h->n_pad * F;
+  const bool use_graph = graphs_enabled() && !h->prof_on && (t_hi - t_lo) > 1;
+  bool on_gstream = false;  // the handle's stream has been ordered after the caller's and has work of this call
   for (int t = t_hi - 1, k = 0; t >= t_lo; --t, ++k) {
     const float* c = &h->coef[(size_t)t * 4];
     fd::StepCoef coef{c[0], c[1], c[2], c[3], t > 0 ? 1 : 0};
@@ -652,10 +726,32 @@ int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise
                         (unsigned long long)(offset + (uint64_t)k * slice)};
     float* hist = history_dev ? history_dev + (size_t)k * slice : nullptr;
     const float* temb = h->time_table + (size_t)t * Hd;
+    const bool have_graph = use_graph && h->gexec && h->graph_gen == h->batch_gen && h->graph_mode == h->gemm_mode &&
+                            h->graph_x == x_dev && h->graph_wrap == wrap_bits;
+    if (have_graph) {
+      if (!on_gstream) {
+        FD_CUDA(cudaEventRecord(h->ev_in, st));
+        FD_CUDA(cudaStreamWaitEvent(h->gstream, h->ev_in, 0));
+        on_gstream = true;
+      }
+      const fd::StepDyn dyn{temb, noise, hist, coef};
+      // pageable source: staged by the driver before the call returns, ordered on the stream behind the previous replay
+      FD_CUDA(cudaMemcpyAsync(h->dyn_dev, &dyn, sizeof(dyn), cudaMemcpyHostToDevice, h->gstream));
+      FD_CUDA(cudaGraphLaunch(h->gexec, h->gstream));
+      h->launches += h->graph_launches;
+      continue;
+    }
 #define FD_STEP(V)                                                                               \
   case V:                                                                                        \
     rc = run_encoder<V>(h, x_dev, temb, 0, st);                                                  \
     if (!rc) launch_tail<V, true>(h, nullptr, x_dev, noise, hist, coef, wrap_bits, st);          \
+    if (!rc && use_graph && !h->graph_broken && t > t_lo) {                                      \
+      if (capture_step_graph<V>(h, x_dev, wrap_bits) == FD_OK) {                                 \
+        h->graph_gen = h->batch_gen; h->graph_mode = h->gemm_mode; h->graph_x = x_dev; h->graph_wrap = wrap_bits; \
+      } else {  /* not fatal: keep launching kernel by kernel, do not try again */               \
+        h->graph_broken = true; h->graph_gen = -1; cudaGetLastError();                           \
+      }                                                                                          \
+    }                                                                                            \
     break;
     switch (Hd / 32) {
       FD_STEP(2) FD_STEP(4) FD_STEP(6) FD_STEP(8) FD_STEP(10) FD_STEP(12) FD_STEP(14) FD_STEP(16)
@@ -664,12 +760,18 @@ int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise
 #undef FD_STEP
     if (rc) return rc;
   }
+  if (on_gstream) {
+    FD_CUDA(cudaEventRecord(h->ev_out, h->gstream));
+    FD_CUDA(cudaStreamWaitEvent(st, h->ev_out, 0));
+  }
   rc = check_launch();
   if (rc) return rc;
   return flag_enqueue_copy(h, st);
 }
 
 }  // namespace
+
+extern "C" {
 
 int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
                           const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
@@ -938,6 +1040,12 @@ int32_t fd_write_batch(int32_t n_chains, const float* angles_host, int32_t n_pad
 }
 
 int32_t fd_debug_tc_status(void) { return fd::tc_check_error(); }
+
+int32_t fd_debug_graph_state(const fd_handle* h) {
+  if (!h) return 0;
+  if (h->graph_broken) return -1;
+  return (h->gexec && h->graph_gen == h->batch_gen) ? 1 : 0;
+}
 
 int32_t fd_debug_attention_dump(float* dump_dev) {
   fd::atc_debug_dump() = dump_dev;

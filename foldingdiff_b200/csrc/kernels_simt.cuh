@@ -20,6 +20,28 @@
 
 namespace fd {
 
+struct StepCoef {
+  float c1, beta, s, sigma;
+  int add_noise;  // t > 0
+};
+// Source of the step's normals z (sampling.py:73): the caller's draws (z != nullptr: slice of the step) or, in the
+// throughput mode, element `offset + b * n_pad * F + n * F + f` of the library's Philox stream `seed` - the same
+// element fd_randn would have written there, so the two paths agree bit for bit.
+struct StepNoise {
+  const float* z;
+  unsigned long long seed, offset;
+};
+// Per-step arguments of a reverse step replayed as a CUDA graph (api.cu: run_steps): the graph's kernel arguments are
+// frozen at capture time, so what changes from step to step - the time-embedding row, the posterior coefficients, the
+// noise slice, the history slice - lives in one small device struct that is rewritten (stream-ordered) before every
+// graph launch.  embed_kernel and tail_kernel read it when their `dyn` argument is non-null.
+struct StepDyn {
+  const float* temb;
+  StepNoise noise;
+  float* hist;
+  StepCoef coef;
+};
+
 // ------------------------------------------------------------------------------------------------
 // embed: h[r, :] = LN(x[b, n, :] @ W_in^T + b_in) * g + beta  +  temb[b, :]
 // one warp per packed row; lane owns columns lane + 32 * i.
@@ -30,7 +52,7 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
              int F, const float* __restrict__ w_in, const float* __restrict__ b_in,
              const float* __restrict__ g, const float* __restrict__ bta, float eps,
              const float* __restrict__ temb, int temb_stride, float* __restrict__ h_out,
-             __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
+             __half* __restrict__ o_hi, __half* __restrict__ o_lo, const StepDyn* __restrict__ dyn) {
   constexpr int H = VPL * 32;
   pdl_trigger();
   pdl_wait();  // x is the previous step's output; h / planes were read by the previous step's kernels
@@ -60,7 +82,7 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
     sq = fmaf(d, d, sq);
   }
   const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / H) + eps);
-  const float* te = temb + (size_t)chain * temb_stride;
+  const float* te = (dyn ? dyn->temb : temb) + (size_t)chain * temb_stride;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
@@ -317,18 +339,6 @@ attention_simt_kernel(const float* __restrict__ qkv, const int* __restrict__ row
 // one warp per packed row.  The posterior arithmetic uses explicitly rounded fp32 ops in the
 // reference's order (multiply by beta, then divide by s) so it is bit-comparable given equal eps.
 // ------------------------------------------------------------------------------------------------
-struct StepCoef {
-  float c1, beta, s, sigma;
-  int add_noise;  // t > 0
-};
-// Source of the step's normals z (sampling.py:73): the caller's draws (z != nullptr: slice of the step) or, in the
-// throughput mode, element `offset + b * n_pad * F + n * F + f` of the library's Philox stream `seed` - the same
-// element fd_randn would have written there, so the two paths agree bit for bit.
-struct StepNoise {
-  const float* z;
-  unsigned long long seed, offset;
-};
-
 template <int VPL, bool SAMPLE>
 __global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ u, const int* __restrict__ row_src, int n_rows, int F,
@@ -336,13 +346,14 @@ tail_kernel(const float* __restrict__ u, const int* __restrict__ row_src, int n_
             const float* __restrict__ w2, const float* __restrict__ b2,
             float* __restrict__ eps_out,                         // MODE_EPS
             float* __restrict__ x, StepNoise noise,              // MODE_SAMPLE
-            float* __restrict__ hist, StepCoef coef, uint32_t wrap_bits) {
+            float* __restrict__ hist, StepCoef coef, uint32_t wrap_bits, const StepDyn* __restrict__ dyn) {
   constexpr int H = VPL * 32;
   pdl_trigger();
   extern __shared__ __align__(16) float w2s[];  // [F][H]
   for (int i = threadIdx.x; i < F * H; i += blockDim.x) w2s[i] = w2[i];  // weights: no dependence on the chain
   __syncthreads();
   pdl_wait();
+  if (SAMPLE && dyn) { noise = dyn->noise; hist = dyn->hist; coef = dyn->coef; }  // graph replay: this step's arguments
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_rows) return;

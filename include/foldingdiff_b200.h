@@ -292,6 +292,11 @@ int32_t fd_write_batch(int32_t n_chains, const float* angles_host, int32_t n_pad
  * MMA issuer / epilogue timed out (the kernels never spin forever). Negative = CUDA error. */
 int32_t fd_debug_tc_status(void);
 
+/* Debug / test hook: 1 = the reverse step of the current batch is being replayed as a CUDA graph (fd_p_sample_steps*
+ * capture it after the first step of a window), 0 = not (yet) captured, -1 = a capture failed and the handle stays on
+ * kernel-by-kernel launches (FOLDINGDIFF_B200_GRAPH=0 also keeps it at 0). */
+int32_t fd_debug_graph_state(const fd_handle* h);
+
 /* Debug / test hook for the tcgen05 attention kernel (FOLDINGDIFF_B200_ATT=tc): while dump_dev is
  * non-NULL every launch also writes, per (chain, head) item and query row, 290 floats
  * {S raw [128], S + relative-key term [128], O unnormalised [32], row max (log2 units), row sum} to

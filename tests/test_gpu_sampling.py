@@ -14,6 +14,8 @@ import numpy as np
 import pytest
 import torch
 
+PI32 = float(np.float32(np.pi))  # the reference wraps in fp32: -float32(pi) is a legal value and |it| > math.pi
+
 from conftest import load_golden
 from gpu_util import GEMMS, mini_model, prod_model
 from foldingdiff_b200 import beta_schedules, datasets, sampling, synthetic
@@ -128,7 +130,7 @@ def test_cosine_config1_chain_statistics(mini_dir, gemm, monkeypatch):
     # de-bias (gemm_tc.cuh: tc_rz), median ~1e-5 / 85-88% with it (profiles/r02_rz_calibration.md); what is left between
     # the two arithmetics is which way the chaotic tail of this ill-conditioned chain falls, not a systematic error
     assert float(d.median()) < 2e-5 and frac > (0.9 if gemm == "fp32" else 0.8)
-    assert float(out.abs().max()) <= np.pi  # every column is angular and wrapped into [-pi, pi)
+    assert float(out.abs().max()) <= PI32  # every column is angular and wrapped into [-pi, pi)
     # distributional agreement of the final structures (SURVEY.md section 8c protocol (4)): per-feature circular mean
     # and dispersion over the 4 x 64 residues must match the reference chain even where single angles have diverged
     def circ_stats(a):
@@ -202,7 +204,7 @@ def test_host_buffer_entry_point_matches_device_path(mini_dir, monkeypatch):
         assert np.array_equal(final[i, :l], dev[-1, i, :l].numpy())
     own = eng.sample_host(lengths, x0.numpy(), T, None, 1234, ANG, full_history=False)  # library Philox stream
     own2 = eng.sample_host(lengths, x0.numpy(), T, None, 1234, ANG, full_history=False)
-    assert np.array_equal(own, own2) and np.isfinite(own).all() and np.abs(own).max() <= np.pi
+    assert np.array_equal(own, own2) and np.isfinite(own).all() and np.abs(own).max() <= PI32
 
 
 @pytest.mark.parametrize("gemm", GEMMS)
@@ -223,7 +225,7 @@ def test_full_size_batch_properties(gemm):
     torch.manual_seed(1)
     z = torch.randn(3, 512, 127, 6, device="cuda")
     eng.p_sample_steps(x, T, T - 3, z, None, ANG)
-    assert bool(torch.isfinite(x).all()) and float(x.abs().max()) <= np.pi
+    assert bool(torch.isfinite(x).all()) and float(x.abs().max()) <= PI32
     # chains are independent: a sub-batch gives the same chains (sharding over GPUs is exact)
     sub = list(range(3, 512, 8))
     xs = noise[sub].cuda().contiguous().clone()
@@ -285,7 +287,7 @@ def test_philox_steps_equal_predrawn_library_noise(mini_dir):
         p2 = sampling.p_sample_loop(model, lengths, x0.cpu(), T, beta_schedules.get_variance_schedule("linear", T), is_angle=ANG)
     finally:
         sampling.set_noise_source("torch")
-    assert torch.equal(p1, p2) and float(p1.abs().max()) <= np.pi and p1.shape == (T, 3, N, 6)
+    assert torch.equal(p1, p2) and float(p1.abs().max()) <= PI32 and p1.shape == (T, 3, N, 6)
 
 
 def test_parity_rng_sharded_ranks_reproduce_the_single_gpu_run(mini_dir):
@@ -308,3 +310,43 @@ def test_parity_rng_sharded_ranks_reproduce_the_single_gpu_run(mini_dir):
                                          history="final", noise_shard=sampling.NoiseShard(5, rows))[-1]
             got[rows] = loc
         assert torch.equal(got, ref), f"world={world}: max diff {float((got - ref).abs().max()):.3e}"
+
+
+def test_graph_replay_equals_kernel_by_kernel_launches(mini_dir):
+    """A window of reverse steps is one eager step + CUDA-graph replays (api.cu: run_steps); with the library's profiler on,
+    every step is launched kernel by kernel.  Same kernels, same order: identical bits - for both noise sources, with a
+    history, across a batch change (the graph is re-captured) and across windows."""
+    from foldingdiff_b200 import _native
+    model = mini_model(mini_dir, "tc3x")
+    eng = model.native_engine()
+    T = 10
+    eng.set_schedule(beta_schedules.get_variance_schedule("cosine", T), T)
+    g = torch.Generator().manual_seed(12)
+    for lengths, N in (([33, 40, 17], 40), ([64, 50], 64)):
+        B = len(lengths)
+        eng.set_batch(lengths, N)
+        x0 = oloop.wrap(torch.randn(B, N, 6, generator=g)).cuda()
+        z = torch.randn(T, B, N, 6, generator=g).cuda()
+        a, b = x0.clone(), x0.clone()
+        ha, hb = torch.zeros(T, B, N, 6, device="cuda"), torch.zeros(T, B, N, 6, device="cuda")
+        eng.profile_begin()                                   # profiler on: no graph
+        eng.p_sample_steps(a, T, 0, z, ha, ANG)
+        eng.profile_end()
+        eng.p_sample_steps(b, T, 4, z[:6].contiguous(), hb[:6], ANG)     # window 1: step 0 eager, steps 1..5 replayed
+        state = _native.lib().fd_debug_graph_state(eng._h)
+        eng.p_sample_steps(b, 4, 0, z[6:].contiguous(), hb[6:], ANG)     # window 2: replays from its first step
+        torch.cuda.synchronize()
+        eng.check_status()
+        assert state in (0, 1), "graph capture failed on this device"
+        import os
+        if os.environ.get("FOLDINGDIFF_B200_GRAPH", "1") != "0":
+            assert state == 1
+        assert torch.equal(a, b) and torch.equal(ha, hb)
+        c = x0.clone()
+        eng.p_sample_steps_philox(c, T, 0, 99, 0, None, ANG)
+        d = x0.clone()
+        eng.profile_begin()
+        eng.p_sample_steps_philox(d, T, 0, 99, 0, None, ANG)
+        eng.profile_end()
+        torch.cuda.synchronize()
+        assert torch.equal(c, d)

@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+PI32 = float(np.float32(np.pi))  # the reference wraps in fp32: -float32(pi) is a legal value and |it| > math.pi
+
 from conftest import load_golden, mini_state_dict
 from foldingdiff_b200 import _native, beta_schedules, datasets, engine, modelling, sampling, utils
 
@@ -83,7 +85,7 @@ def test_forward_noising_getitem():
     assert it["corrupted"].shape == (32, 6) and int(it["t"]) == 10
     expect = it["sqrt_alphas_cumprod_t"] * it["angles"] + it["sqrt_one_minus_alphas_cumprod_t"] * it["known_noise"]
     assert torch.allclose(it["corrupted"], utils.modulo_with_wrapped_range(expect), atol=1e-6)
-    assert float(it["corrupted"].abs().max()) <= np.pi
+    assert float(it["corrupted"].abs().max()) <= PI32
 
 
 def test_from_dir_loads_checkpoint_strictly(mini_dir, tmp_path):
