@@ -736,8 +736,13 @@ int run_steps(fd_handle* h, float* x_dev, int t_hi, int t_lo, const float* noise
       }
       const fd::StepDyn dyn{temb, noise, hist, coef};
       // pageable source: staged by the driver before the call returns, ordered on the stream behind the previous replay
-      FD_CUDA(cudaMemcpyAsync(h->dyn_dev, &dyn, sizeof(dyn), cudaMemcpyHostToDevice, h->gstream));
-      FD_CUDA(cudaGraphLaunch(h->gexec, h->gstream));
+      cudaError_t ge = cudaMemcpyAsync(h->dyn_dev, &dyn, sizeof(dyn), cudaMemcpyHostToDevice, h->gstream);
+      if (ge == cudaSuccess) ge = cudaGraphLaunch(h->gexec, h->gstream);
+      if (ge != cudaSuccess) {  // keep the caller's stream ordered behind whatever was enqueued before reporting
+        cudaEventRecord(h->ev_out, h->gstream);
+        cudaStreamWaitEvent(st, h->ev_out, 0);
+        return fail(FD_ERR_CUDA, "step graph replay failed: %s", cudaGetErrorString(ge));
+      }
       h->launches += h->graph_launches;
       continue;
     }
