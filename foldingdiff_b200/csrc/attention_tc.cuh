@@ -272,12 +272,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         uint8_t* s = ring + (size_t)slot * ATC_SLOT_BYTES;
         const int cq = a.head * FD_HEAD_DIM;
         mbar_expect_tx(&kv_full[slot], ATC_SLOT_BYTES);
-        tma_load_2d(s, &map_hi, &kv_full[slot], cq, a.r0);
-        tma_load_2d(s + 2 * ATC_PLANE_BYTES, &map_hi, &kv_full[slot], H + cq, a.r0);
-        tma_load_2d(s + 1 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], cq, a.r0);
-        tma_load_2d(s + 3 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], H + cq, a.r0);
-        tma_load_2d(s + 4 * ATC_PLANE_BYTES, &map_hi, &kv_full[slot], 2 * H + cq, a.r0);
-        tma_load_2d(s + 5 * ATC_PLANE_BYTES, &map_lo, &kv_full[slot], 2 * H + cq, a.r0);
+        // Q / K / V planes are read exactly once (by this kernel): evict-first keeps the 206 MB stream from pushing the
+        // ctx planes written below - the next GEMM's A operand - out of the 126 MB L2
+#ifdef ATC_NO_EVICT_HINT
+#define ATC_TMA(dst, map, col) tma_load_2d(dst, map, &kv_full[slot], col, a.r0)
+#else
+#define ATC_TMA(dst, map, col) tma_load_2d_hint(dst, map, &kv_full[slot], col, a.r0, TC_EVICT_FIRST)
+#endif
+        ATC_TMA(s, &map_hi, cq);
+        ATC_TMA(s + 2 * ATC_PLANE_BYTES, &map_hi, H + cq);
+        ATC_TMA(s + 1 * ATC_PLANE_BYTES, &map_lo, cq);
+        ATC_TMA(s + 3 * ATC_PLANE_BYTES, &map_lo, H + cq);
+        ATC_TMA(s + 4 * ATC_PLANE_BYTES, &map_hi, 2 * H + cq);
+        ATC_TMA(s + 5 * ATC_PLANE_BYTES, &map_lo, 2 * H + cq);
+#undef ATC_TMA
       }
     }
   } else if (warp == 9) {

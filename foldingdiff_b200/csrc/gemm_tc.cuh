@@ -129,6 +129,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                uint16_t cta_mask) {
   asm volatile(
@@ -288,8 +295,14 @@ struct TcCfg {
 };
 
 // four consecutive residual-source values
+// (streaming load: the fp32 rows of a LayerNorm site are read exactly once, by the next site's epilogue, long after
+// they have left L2 - they must not displace the hi / lo planes the NEXT kernel is about to read)
 __device__ __forceinline__ float4 tc_load_res4(const TcLn& ln, const float* plain, size_t off) {
+#ifdef TC_NO_STREAM_HINTS
   return *reinterpret_cast<const float4*>((plain ? plain : ln.res_v) + off);
+#else
+  return __ldcs(reinterpret_cast<const float4*>((plain ? plain : ln.res_v) + off));
+#endif
 }
 
 template <int BN, int NPASS, int EPI, int CL, bool PAIR>
@@ -582,7 +595,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             s2[i] = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, s2[i]))));
           }
           if (EPI == EPI_BIAS_GELU || EPI == EPI_LNIN_GELU) { o0 = gelu_erf_fast(o0); o1 = gelu_erf_fast(o1); o2 = gelu_erf_fast(o2); o3 = gelu_erf_fast(o3); }
+#ifdef TC_NO_STREAM_HINTS
           if (C) *reinterpret_cast<float4*>(C + off) = make_float4(o0, o1, o2, o3);
+#else
+          if (C) __stcs(reinterpret_cast<float4*>(C + off), make_float4(o0, o1, o2, o3));  // read once, three kernels later
+#endif
           if (c_hi) {
             const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
             uint2 ph;
