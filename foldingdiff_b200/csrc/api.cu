@@ -166,9 +166,10 @@ void free_batch(fd_handle* h) {
 template <int VPL>
 void launch_embed(fd_handle* H, const float* x, const float* temb, int temb_stride, fd::TcPlane* planes,
                   cudaStream_t st, const fd::StepDyn* dyn = nullptr) {
-  const int blocks = (H->rows * 32 + 255) / 256;
+  const int want = (H->rows + 3) / 4, cap = H->sm_count * 3;  // persistent warps: 4 per block, 3 blocks per SM
+  const int blocks = want < cap ? want : cap;
   ProfScope ps(H, CAT_EMBED, st);
-  fd::launch_pdl(fd::embed_kernel<VPL>, dim3(blocks), dim3(256), 0, st, x, H->row_src, H->rows, H->n_pad, H->d.n_features,
+  fd::launch_pdl(fd::embed_kernel<VPL>, dim3(blocks), dim3(128), 0, st, x, H->row_src, H->rows, H->n_pad, H->d.n_features,
                  H->w_in, H->b_in, H->emb_g, H->emb_b, H->d.ln_eps, temb, temb_stride, H->h,
                  planes ? planes->hi : (__half*)nullptr,
                  (planes && H->gemm_mode == FD_GEMM_TC_3X) ? planes->lo : (__half*)nullptr, dyn);
@@ -241,7 +242,8 @@ int launch_attention_mma(fd_handle* H, const LayerW& w, cudaStream_t st) {
 template <int VPL, bool SAMPLE>
 void launch_tail(fd_handle* H, float* eps_out, float* x, fd::StepNoise noise, float* hist,
                  fd::StepCoef coef, uint32_t wrap_bits, cudaStream_t st, const fd::StepDyn* dyn = nullptr) {
-  const int blocks = (H->rows * 32 + 255) / 256;
+  const int want = (H->rows + 7) / 8, cap = H->sm_count * 4;  // persistent warps (kernels_simt.cuh: tail_kernel)
+  const int blocks = want < cap ? want : cap;
   const size_t smem = sizeof(float) * H->d.n_features * H->d.hidden;
   ProfScope ps(H, CAT_TAIL, st);
   fd::launch_pdl(fd::tail_kernel<VPL, SAMPLE>, dim3(blocks), dim3(256), smem, st, (const float*)H->tmp,

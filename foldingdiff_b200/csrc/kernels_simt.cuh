@@ -44,10 +44,16 @@ struct StepDyn {
 
 // ------------------------------------------------------------------------------------------------
 // embed: h[r, :] = LN(x[b, n, :] @ W_in^T + b_in) * g + beta  +  temb[b, :]
-// one warp per packed row; lane owns columns lane + 32 * i.
+// One warp per packed row at a time, lane owns columns lane + 32 * i; the warps are PERSISTENT (grid-stride over
+// the rows) and keep everything that does not depend on the row in registers - the input projection (F <= 6 features:
+// every shipped model has 6), its bias, the LayerNorm vectors and, in the sampling loop where every chain shares the
+// step's time embedding, that row too.  (Round 1 launched one warp per row and re-read ~100 weights per row through
+// L1: 90 us per reverse step for 137 MB of output, a quarter of the HBM rate.)
 // ------------------------------------------------------------------------------------------------
+constexpr int EMBED_FR = 6;  // features whose projection weights are held in registers (every shipped feature set has <= 6)
+
 template <int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n_rows, int n_pad,
              int F, const float* __restrict__ w_in, const float* __restrict__ b_in,
              const float* __restrict__ g, const float* __restrict__ bta, float eps,
@@ -55,43 +61,63 @@ embed_kernel(const float* __restrict__ x, const int* __restrict__ row_src, int n
              __half* __restrict__ o_hi, __half* __restrict__ o_lo, const StepDyn* __restrict__ dyn) {
   constexpr int H = VPL * 32;
   pdl_trigger();
-  pdl_wait();  // x is the previous step's output; h / planes were read by the previous step's kernels
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= n_rows) return;
-  const int src = row_src[warp];
-  const int chain = src / n_pad;
-  float xin[FD_MAX_FEATURES];
-#pragma unroll
-  for (int f = 0; f < FD_MAX_FEATURES; ++f) xin[f] = (f < F) ? x[(size_t)src * F + f] : 0.0f;
-  float v[VPL];
-  float sum = 0.0f;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const bool wreg = F <= EMBED_FR;
+  float w[VPL][EMBED_FR], bi[VPL], gg[VPL], bb[VPL];  // weights: independent of the chain of kernels
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
-    float a = 0.0f;
-    for (int f = 0; f < F; ++f) a = fmaf(xin[f], w_in[c * F + f], a);
-    v[i] = a + b_in[c];
-    sum += v[i];
-  }
-  const float mean = warp_sum(sum) * (1.0f / H);
-  float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float d = v[i] - mean;
-    sq = fmaf(d, d, sq);
+    for (int f = 0; f < EMBED_FR; ++f) w[i][f] = (wreg && f < F) ? w_in[c * F + f] : 0.0f;
+    bi[i] = b_in[c]; gg[i] = g[c]; bb[i] = bta[c];
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / H) + eps);
-  const float* te = (dyn ? dyn->temb : temb) + (size_t)chain * temb_stride;
+  pdl_wait();  // x is the previous step's output; h / planes were read by the previous step's kernels
+  const float* te0 = dyn ? dyn->temb : temb;
+  float tev[VPL];
+  if (temb_stride == 0) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = lane + 32 * i;
-    const float y = ((v[i] - mean) * rstd) * g[c] + bta[c] + te[c];
-    h_out[(size_t)warp * H + c] = y;
-    if (o_hi) {  // fp16 hi / lo operand planes for the tensor-core GEMM that consumes this row
-      const __half hh = __float2half_rn(y);
-      o_hi[(size_t)warp * H + c] = hh;
-      if (o_lo) o_lo[(size_t)warp * H + c] = __float2half_rn(y - __half2float(hh));
+    for (int i = 0; i < VPL; ++i) tev[i] = te0[lane + 32 * i];
+  }
+  for (int r = gw; r < n_rows; r += nw) {
+    const int src = row_src[r];
+    float xin[EMBED_FR];
+#pragma unroll
+    for (int f = 0; f < EMBED_FR; ++f) xin[f] = (f < F) ? x[(size_t)src * F + f] : 0.0f;
+    float v[VPL];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float a = 0.0f;
+      if (wreg) {  // zero weights beyond F leave the sum untouched: same fp32 operations, same order, as a loop over F
+#pragma unroll
+        for (int f = 0; f < EMBED_FR; ++f) a = fmaf(xin[f], w[i][f], a);
+      } else {
+        const int c = lane + 32 * i;
+        for (int f = 0; f < F; ++f) a = fmaf(x[(size_t)src * F + f], w_in[c * F + f], a);
+      }
+      v[i] = a + bi[i];
+      sum += v[i];
+    }
+    const float mean = warp_sum(sum) * (1.0f / H);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float d = v[i] - mean;
+      sq = fmaf(d, d, sq);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / H) + eps);
+    const float* te = te0 + (size_t)(src / n_pad) * temb_stride;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      const float y = ((v[i] - mean) * rstd) * gg[i] + bb[i] + (temb_stride == 0 ? tev[i] : te[c]);
+      h_out[(size_t)r * H + c] = y;
+      if (o_hi) {  // fp16 hi / lo operand planes for the tensor-core GEMM that consumes this row
+        const __half hh = __float2half_rn(y);
+        o_hi[(size_t)r * H + c] = hh;
+        if (o_lo) o_lo[(size_t)r * H + c] = __float2half_rn(y - __half2float(hh));
+      }
     }
   }
 }
@@ -351,54 +377,56 @@ tail_kernel(const float* __restrict__ u, const int* __restrict__ row_src, int n_
   pdl_trigger();
   extern __shared__ __align__(16) float w2s[];  // [F][H]
   for (int i = threadIdx.x; i < F * H; i += blockDim.x) w2s[i] = w2[i];  // weights: no dependence on the chain
+  const int lane = threadIdx.x & 31;
+  float gg[VPL], bb[VPL];  // head LayerNorm vectors: weights, fetched before the wait
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { gg[i] = g[lane + 32 * i]; bb[i] = bta[lane + 32 * i]; }
   __syncthreads();
   pdl_wait();
   if (SAMPLE && dyn) { noise = dyn->noise; hist = dyn->hist; coef = dyn->coef; }  // graph replay: this step's arguments
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_rows) return;
-  float v[VPL];
-  float sum = 0.0f;
+  // persistent warps: the 9 KB of dense2 weights are staged once per block, not once per 8 rows
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < n_rows; r += nw) {
+    float v[VPL];
+    float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i] = u[(size_t)warp * H + lane + 32 * i];
-    sum += v[i];
-  }
-  const float mean = warp_sum(sum) * (1.0f / H);
-  float sq = 0.0f;
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = u[(size_t)r * H + lane + 32 * i];
+      sum += v[i];
+    }
+    const float mean = warp_sum(sum) * (1.0f / H);
+    float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float d = v[i] - mean;
-    sq = fmaf(d, d, sq);
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / H) + eps_ln);
+    for (int i = 0; i < VPL; ++i) {
+      const float d = v[i] - mean;
+      sq = fmaf(d, d, sq);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / H) + eps_ln);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = ((v[i] - mean) * rstd) * g[c] + bta[c];
-  }
-  float mine = 0.0f;  // lane f keeps eps[f]
-  for (int f = 0; f < F; ++f) {
-    float p = 0.0f;
+    for (int i = 0; i < VPL; ++i) v[i] = ((v[i] - mean) * rstd) * gg[i] + bb[i];
+    float mine = 0.0f;  // lane f keeps eps[f]
+    for (int f = 0; f < F; ++f) {
+      float p = 0.0f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) p = fmaf(v[i], w2s[f * H + lane + 32 * i], p);
-    p = warp_sum(p);
-    if (lane == f) mine = p + b2[f];
-  }
-  if (lane < F) {
-    const size_t idx = (size_t)row_src[warp] * F + lane;
-    if (!SAMPLE) {
-      eps_out[idx] = mine;
-    } else {
-      const float xv = x[idx];
-      float y = __fmul_rn(coef.c1, __fsub_rn(xv, __fdiv_rn(__fmul_rn(coef.beta, mine), coef.s)));
-      if (coef.add_noise) {
-        const float zv = noise.z ? noise.z[idx] : philox_normal(noise.seed, noise.offset + idx);
-        y = __fadd_rn(y, __fmul_rn(coef.sigma, zv));
+      for (int i = 0; i < VPL; ++i) p = fmaf(v[i], w2s[f * H + lane + 32 * i], p);
+      p = warp_sum(p);
+      if (lane == f) mine = p + b2[f];
+    }
+    if (lane < F) {
+      const size_t idx = (size_t)row_src[r] * F + lane;
+      if (!SAMPLE) {
+        eps_out[idx] = mine;
+      } else {
+        const float xv = x[idx];
+        float y = __fmul_rn(coef.c1, __fsub_rn(xv, __fdiv_rn(__fmul_rn(coef.beta, mine), coef.s)));
+        if (coef.add_noise) {
+          const float zv = noise.z ? noise.z[idx] : philox_normal(noise.seed, noise.offset + idx);
+          y = __fadd_rn(y, __fmul_rn(coef.sigma, zv));
+        }
+        if ((wrap_bits >> lane) & 1u) y = wrap_pi(y);
+        x[idx] = y;
+        if (hist) hist[idx] = y;
       }
-      if ((wrap_bits >> lane) & 1u) y = wrap_pi(y);
-      x[idx] = y;
-      if (hist) hist[idx] = y;
     }
   }
 }
