@@ -180,6 +180,10 @@ int32_t fd_forward(fd_handle* h, const float* x_dev, const float* temb_dev, floa
  *   history_dev : NULL, or (t_hi - t_lo, batch, n_pad, F): slice k = x after step k
  *                 (the reference's imgs list, sampling.py:131-132)
  *   wrap_mask   : HOST uint8[F]
+ * Execution: the first step of a new (batch, arithmetic, x buffer, wrap mask) combination is launched kernel by
+ * kernel on `stream`; the step is then captured once into a CUDA graph on a stream the handle owns and every
+ * further step is one graph launch (FOLDINGDIFF_B200_GRAPH=0 disables).  The handle's stream is ordered after
+ * `stream` on entry and `stream` after it on exit, so the stream contract above holds unchanged.
  */
 int32_t fd_p_sample_steps(fd_handle* h, float* x_dev, int32_t t_hi, int32_t t_lo,
                           const float* noise_dev, float* history_dev, const uint8_t* wrap_mask,
