@@ -157,3 +157,26 @@ def test_weight_key_order_matches_header():
     assert len(keys) == _native.W_HEAD + 6 * _native.W_PER_LAYER + _native.W_TAIL == 112
     assert set(keys) == set(sd) - {"time_embed.W"}
     assert keys[4 + 17 + 6] == "encoder.layer.1.attention.self.distance_embedding.weight"
+
+
+def test_cli_argument_checks_run_before_any_device_or_process_group_work(tmp_path):
+    """bin/sample.py: a bad invocation ends at once with the reference's messages - before CUDA, before torch.distributed
+    (under torchrun a rank-0 failure after init_process_group would leave the other ranks in a collective)."""
+    import subprocess
+    import sys
+    from conftest import ROOT, mini_state_dict, write_model_dir
+    cli = os.path.join(ROOT, "bin", "sample.py")
+    res = subprocess.run([sys.executable, cli, "-m", str(tmp_path / "missing"), "-o", str(tmp_path / "o1")], capture_output=True, text=True)
+    assert res.returncode != 0 and "is not a directory" in res.stderr
+    sd, cfg, targs, ckpt = mini_state_dict()
+    mdir = write_model_dir(str(tmp_path / "model"), sd, cfg, targs, ckpt)
+    busy = tmp_path / "busy"
+    busy.mkdir()
+    (busy / "leftover.txt").write_text("x")
+    res = subprocess.run([sys.executable, cli, "-m", mdir, "-o", str(busy)], capture_output=True, text=True)
+    assert res.returncode != 0 and "to be empty" in res.stderr
+    res = subprocess.run([sys.executable, cli, "-m", mdir, "-o", str(tmp_path / "o2"), "--testcomparison"], capture_output=True, text=True)
+    assert res.returncode != 0 and "CATH" in res.stderr
+    env = dict(os.environ, WORLD_SIZE="2", RANK="0", LOCAL_RANK="0")
+    res = subprocess.run([sys.executable, cli, "-m", mdir, "-o", str(tmp_path / "o3"), "--fullhistory"], capture_output=True, text=True, env=env)
+    assert res.returncode != 0 and "single-GPU only" in res.stderr
