@@ -68,9 +68,10 @@ def sample_final_sharded(model, lengths: Sequence[int], noise: torch.Tensor, tim
     """
     from . import sampling
 
+    if rng not in ("parity", "perf"):
+        raise ValueError(f"rng must be 'parity' or 'perf', got {rng!r}")
     rank, world = _world(group)
     shard = sampling.NoiseShard(len(lengths), shard_indices(len(lengths), rank, world)) if rng == "parity" else None
-    assert rng in ("parity", "perf"), rng
 
     def run(local_lengths, local_noise):
         dev = next(model.parameters()).device
