@@ -60,3 +60,16 @@ def test_algorithmic_flops_match_survey_table():
     f = synthetic.algorithmic_flops(synthetic.PRODUCTION, lengths)
     assert abs(f - 1.3895e12) / 1.3895e12 < 1e-3
     assert abs(synthetic.algorithmic_flops(synthetic.PRODUCTION, [128]) - 4.1158e9) / 4.1158e9 < 1e-4
+
+
+def test_every_tool_script_parses():
+    """tools/*.py compile and tools/*.sh pass `bash -n` (they only ever run on the GPU box, where a typo costs a call)."""
+    import glob
+    import py_compile
+    import subprocess
+    tools = os.path.join(ROOT, "tools")
+    for f in sorted(glob.glob(os.path.join(tools, "*.py"))):
+        py_compile.compile(f, doraise=True)
+    for f in sorted(glob.glob(os.path.join(tools, "*.sh"))):
+        r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stderr)
